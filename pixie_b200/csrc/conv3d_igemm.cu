@@ -1,0 +1,535 @@
+// tcgen05 implicit-GEMM Conv3d for sm_100a: kernel + host planning. See conv3d_igemm.cuh.
+#include "conv3d_igemm.cuh"
+#include "ptx.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+
+namespace pixie {
+
+using namespace ptx;
+
+namespace {
+
+constexpr int kMaxWStages = 2;
+constexpr int kMaxSStages = 8;
+
+struct SmemCtrl {
+    uint64_t wfull[kMaxWStages];
+    uint64_t wempty[kMaxWStages];
+    uint64_t sfull[kMaxSStages];
+    uint64_t sempty[kMaxSStages];
+    uint64_t tfull[2];
+    uint64_t tempty[2];
+    uint32_t tmem_base;
+    int abort_flag;
+};
+
+struct TileCoord {
+    int nb, d0, h0, w0, n0, ph_begin, ph_end, split, tde;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const ConvKernelParams& p, int wi) {
+    TileCoord t;
+    t.split = wi % p.split_k;
+    int rest = wi / p.split_k;
+    int nt = rest % p.n_tiles;
+    int m = rest / p.n_tiles;
+    int tw = m % p.tiles_w;
+    m /= p.tiles_w;
+    int th = m % p.tiles_h;
+    m /= p.tiles_h;
+    int td = m % p.tiles_d;
+    t.nb = m / p.tiles_d;
+    t.d0 = td * p.TD;
+    t.h0 = th * p.TH;
+    t.w0 = tw * p.TW;
+    t.n0 = nt * p.block_n;
+    t.ph_begin = (int)(((long long)t.split * p.n_phases) / p.split_k);
+    t.ph_end = (int)(((long long)(t.split + 1) * p.n_phases) / p.split_k);
+    t.tde = min(p.TD, p.D - t.d0);
+    return t;
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv3d_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // dynamic smem base is only guaranteed 16 B aligned by the ABI: align manually to 1024 B
+    uint8_t* smem = reinterpret_cast<uint8_t*>(
+        (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint8_t* w_smem = smem;
+    uint8_t* s_smem = smem + (size_t)p.w_stages * p.w_stage_bytes;
+    SmemCtrl* ctl = reinterpret_cast<SmemCtrl*>(s_smem + (size_t)p.s_stages * p.s_stage_bytes);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int total_items = p.NB * p.tiles_d * p.tiles_h * p.tiles_w * p.n_tiles * p.split_k;
+    const uint32_t tmem_cols_needed = (uint32_t)(p.acc_sets * p.TD * p.block_n);
+    uint32_t tmem_cols = 32;
+    while (tmem_cols < tmem_cols_needed) tmem_cols <<= 1;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kMaxWStages; ++i) { mbar_init(&ctl->wfull[i], 1); mbar_init(&ctl->wempty[i], 1); }
+        for (int i = 0; i < kMaxSStages; ++i) { mbar_init(&ctl->sfull[i], 1); mbar_init(&ctl->sempty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&ctl->tfull[i], 1); mbar_init(&ctl->tempty[i], 4); }
+        ctl->abort_flag = 0;
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(&ctl->tmem_base, tmem_cols);
+        tmem_relinquish();
+    }
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < kConvMaxSrc; ++i) prefetch_tmap(&p.tmA[i]);
+        prefetch_tmap(&p.tmB);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = ctl->tmem_base;
+    volatile int* abort_flag = &ctl->abort_flag;
+
+    if (warp == 0) {
+        // ================================================================ TMA producer
+        if (lane == 0) {
+            int ws = 0, wph = 0, ss = 0, sph = 0;
+            bool ok = true;
+            for (int wi = blockIdx.x; wi < total_items && ok; wi += gridDim.x) {
+                const TileCoord t = decode_tile(p, wi);
+                for (int ph = t.ph_begin; ph < t.ph_end && ok; ++ph) {
+                    const ConvPhase P = p.phases[ph];
+                    const int ntaps = P.n_kh * P.n_kd;
+                    ok = mbar_wait(&ctl->wempty[ws], wph ^ 1, abort_flag);
+                    if (!ok) break;
+                    mbar_expect_tx(&ctl->wfull[ws], (uint32_t)(ntaps * p.block_n * 128));
+                    uint8_t* wdst = w_smem + (size_t)ws * p.w_stage_bytes;
+                    for (int tap = 0; tap < ntaps; ++tap)
+                        tma_load_2d(wdst + (size_t)tap * p.block_n * 128, &p.tmB, &ctl->wfull[ws],
+                                    (P.wtile_base + tap) * 64, t.n0);
+                    if (++ws == p.w_stages) { ws = 0; wph ^= 1; }
+
+                    const int nplanes = t.tde + P.n_kd - 1;
+                    const uint32_t slab_bytes = (uint32_t)p.slab_rows[P.src] * 128u;
+                    for (int pl = 0; pl < nplanes && ok; ++pl) {
+                        ok = mbar_wait(&ctl->sempty[ss], sph ^ 1, abort_flag);
+                        if (!ok) break;
+                        mbar_expect_tx(&ctl->sfull[ss], slab_bytes);
+                        tma_load_5d(s_smem + (size_t)ss * p.s_stage_bytes, &p.tmA[P.src],
+                                    &ctl->sfull[ss], (int)P.c0, t.w0 * p.stride + P.dw,
+                                    t.h0 * p.stride + P.dh0, (t.d0 + pl) * p.stride + P.dd0, t.nb);
+                        if (++ss == p.s_stages) { ss = 0; sph ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================================================ MMA issuer
+        if (lane == 0) {
+            int ws = 0, wph = 0, ss = 0, sph = 0, as = 0, aph = 0;
+            const uint32_t idesc = make_idesc_f16(128, (uint32_t)p.block_n);
+            const uint64_t hi_xor = p.desc_xor;
+            bool ok = true;
+            for (int wi = blockIdx.x; wi < total_items && ok; wi += gridDim.x) {
+                const TileCoord t = decode_tile(p, wi);
+                ok = mbar_wait(&ctl->tempty[as], aph ^ 1, abort_flag);
+                if (!ok) break;
+                tc_fence_after();
+                uint32_t touched = 0;
+                for (int ph = t.ph_begin; ph < t.ph_end && ok; ++ph) {
+                    const ConvPhase P = p.phases[ph];
+                    ok = mbar_wait(&ctl->wfull[ws], wph, abort_flag);
+                    if (!ok) break;
+                    const uint32_t w_addr = smem_u32(w_smem + (size_t)ws * p.w_stage_bytes);
+                    const int nplanes = t.tde + P.n_kd - 1;
+                    for (int pl = 0; pl < nplanes && ok; ++pl) {
+                        ok = mbar_wait(&ctl->sfull[ss], sph, abort_flag);
+                        if (!ok) break;
+                        tc_fence_after();
+                        const uint32_t s_addr = smem_u32(s_smem + (size_t)ss * p.s_stage_bytes);
+                        for (int kd = 0; kd < P.n_kd; ++kd) {
+                            const int d = pl - kd;
+                            if (d < 0 || d >= t.tde) continue;
+                            const uint32_t acc = tmem_base + (uint32_t)((as * p.TD + d) * p.block_n);
+                            for (int kh = 0; kh < P.n_kh; ++kh) {
+                                const int tap = kd * P.n_kh + kh;
+                                const uint32_t a_base = s_addr + (uint32_t)(kh * p.TW * 128);
+                                const uint32_t b_base = w_addr + (uint32_t)(tap * p.block_n * 128);
+#pragma unroll
+                                for (int k4 = 0; k4 < 4; ++k4) {
+                                    const uint64_t da = make_sw128_desc(a_base + k4 * 32, 1024) ^ hi_xor;
+                                    const uint64_t db = make_sw128_desc(b_base + k4 * 32, 1024) ^ hi_xor;
+                                    umma_f16(acc, da, db, idesc, (touched >> d) & 1u);
+                                    touched |= (1u << d);
+                                }
+                            }
+                        }
+                        umma_commit(&ctl->sempty[ss]);   // slab slot free once these MMAs retire
+                        if (++ss == p.s_stages) { ss = 0; sph ^= 1; }
+                    }
+                    umma_commit(&ctl->wempty[ws]);
+                    if (++ws == p.w_stages) { ws = 0; wph ^= 1; }
+                }
+                umma_commit(&ctl->tfull[as]);             // accumulators complete
+                if (++as == p.acc_sets) { as = 0; aph ^= 1; }
+            }
+        }
+    } else {
+        // ================================================================ epilogue (warps 2..5)
+        const int q = warp & 3;                 // TMEM lane quarter this warp may access
+        const int r = q * 32 + lane;            // accumulator row = voxel inside the plane tile
+        const int th = r / p.TW, tw = r % p.TW;
+        int as = 0, aph = 0;
+        bool ok = true;
+        const long long DHW = (long long)p.D * p.H * p.W;
+        for (int wi = blockIdx.x; wi < total_items && ok; wi += gridDim.x) {
+            const TileCoord t = decode_tile(p, wi);
+            ok = mbar_wait(&ctl->tfull[as], aph, abort_flag);
+            if (!ok) break;
+            tc_fence_after();
+            const int hh = t.h0 + th, ww = t.w0 + tw;
+            const bool row_ok = (hh < p.H) && (ww < p.W);
+            const bool first_split = (t.split == 0);
+            for (int d = 0; d < t.tde; ++d) {
+                const long long vox = ((long long)(t.d0 + d) * p.H + hh) * p.W + ww;   // inside batch item
+                const uint32_t acc = tmem_base + ((uint32_t)(q * 32) << 16) +
+                                     (uint32_t)((as * p.TD + d) * p.block_n);
+                for (int c = 0; c < p.block_n; c += 16) {
+                    uint32_t v[16];
+                    tmem_ld16(acc + (uint32_t)c, v);
+                    tmem_ld_wait();
+                    const int ch0 = t.n0 + c;
+                    if (!row_ok || ch0 >= p.Cout) continue;
+                    float f[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+                    if (first_split && p.bias) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (ch0 + j < p.Cout) f[j] += __ldg(p.bias + ch0 + j);
+                    }
+                    if (p.out_planar) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            if (ch0 + j >= p.Cout) break;
+                            const long long idx = ((long long)t.nb * p.Cout + ch0 + j) * DHW + vox;
+                            float val = f[j];
+                            if (first_split && p.residual) val += p.residual[idx];
+                            if (p.atomic_out) atomicAdd(p.out + idx, val);
+                            else p.out[idx] = val;
+                        }
+                    } else {
+                        const long long base = ((long long)t.nb * DHW + vox) * p.out_ld + p.out_c0 + ch0;
+                        if (ch0 + 16 <= p.Cout && ((base & 3) == 0)) {
+                            if (first_split && p.residual) {
+                                const float4* rp = reinterpret_cast<const float4*>(p.residual + base);
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const float4 rv = __ldg(rp + j);
+                                    f[4 * j + 0] += rv.x; f[4 * j + 1] += rv.y;
+                                    f[4 * j + 2] += rv.z; f[4 * j + 3] += rv.w;
+                                }
+                            }
+                            if (p.atomic_out) {
+#pragma unroll
+                                for (int j = 0; j < 4; ++j)
+                                    red_add_v4(p.out + base + 4 * j, f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                            } else {
+                                float4* op = reinterpret_cast<float4*>(p.out + base);
+#pragma unroll
+                                for (int j = 0; j < 4; ++j)
+                                    op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                if (ch0 + j >= p.Cout) break;
+                                float val = f[j];
+                                if (first_split && p.residual) val += p.residual[base + j];
+                                if (p.atomic_out) atomicAdd(p.out + base + j, val);
+                                else p.out[base + j] = val;
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ctl->tempty[as]);
+            if (++as == p.acc_sets) { as = 0; aph ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x == 0 && ctl->abort_flag && p.err_flag) atomicExch(p.err_flag, 1 + (int)blockIdx.x);
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, tmem_cols);
+    }
+}
+
+// =====================================================================================  host side
+
+int conv_k_total(const ConvDesc& d) {
+    int k = 0;
+    for (const auto& s : d.segs) k += s.ks * s.ks * s.ks * d.srcs[s.src].C;
+    return k;
+}
+
+// Source slots: a (source, kernel-size class) pair needs its own tensor map because the TMA box
+// height differs (TH+2 rows for in-slab kh taps vs TH rows).  Slot i of the returned table is used
+// as ConvPhase::src.
+struct SrcSlot { int src; int n_kh; };
+
+static std::vector<SrcSlot> conv_src_slots(const ConvDesc& d) {
+    std::vector<SrcSlot> slots;
+    for (const auto& s : d.segs) {
+        const int n_kh = (s.ks == 3 && d.stride == 1) ? 3 : 1;
+        bool found = false;
+        for (const auto& sl : slots) found |= (sl.src == s.src && sl.n_kh == n_kh);
+        if (!found) slots.push_back({s.src, n_kh});
+    }
+    return slots;
+}
+
+static int conv_slot_of(const std::vector<SrcSlot>& slots, int src, int n_kh) {
+    for (size_t i = 0; i < slots.size(); ++i)
+        if (slots[i].src == src && slots[i].n_kh == n_kh) return (int)i;
+    return -1;
+}
+
+std::vector<ConvPhase> conv_build_phases(const ConvDesc& d) {
+    std::vector<ConvPhase> ph;
+    const auto slots = conv_src_slots(d);
+    int wtile = 0;
+    for (const auto& s : d.segs) {
+        const ConvSrc& src = d.srcs[s.src];
+        const int chunks = src.C / 64;
+        if (s.ks == 1) {
+            for (int c = 0; c < chunks; ++c) {
+                ConvPhase P{};
+                P.src = (int8_t)conv_slot_of(slots, s.src, 1);
+                P.dw = 0; P.dh0 = 0; P.dd0 = 0; P.n_kh = 1; P.n_kd = 1;
+                P.c0 = (int16_t)(c * 64); P.wtile_base = wtile; wtile += 1;
+                ph.push_back(P);
+            }
+        } else if (d.stride == 1) {
+            for (int c = 0; c < chunks; ++c)
+                for (int kw = 0; kw < 3; ++kw) {
+                    ConvPhase P{};
+                    P.src = (int8_t)conv_slot_of(slots, s.src, 3);
+                    P.dw = (int8_t)(kw - 1); P.dh0 = -1; P.dd0 = -1; P.n_kh = 3; P.n_kd = 3;
+                    P.c0 = (int16_t)(c * 64); P.wtile_base = wtile; wtile += 9;
+                    ph.push_back(P);
+                }
+        } else {
+            for (int c = 0; c < chunks; ++c)
+                for (int kw = 0; kw < 3; ++kw)
+                    for (int kh = 0; kh < 3; ++kh)
+                        for (int kd = 0; kd < 3; ++kd) {
+                            ConvPhase P{};
+                            P.src = (int8_t)conv_slot_of(slots, s.src, 1);
+                            P.dw = (int8_t)(kw - 1); P.dh0 = (int8_t)(kh - 1); P.dd0 = (int8_t)(kd - 1);
+                            P.n_kh = 1; P.n_kd = 1;
+                            P.c0 = (int16_t)(c * 64); P.wtile_base = wtile; wtile += 1;
+                            ph.push_back(P);
+                        }
+        }
+    }
+    return ph;
+}
+
+void conv_pack_weights(const ConvDesc& d, const std::vector<const float*>& seg_weights,
+                       const std::vector<int>& seg_cin_real, std::vector<__half>& packed) {
+    const int K = conv_k_total(d);
+    packed.assign((size_t)d.Cout_pad * K, __float2half(0.f));
+    int wtile = 0;
+    for (size_t si = 0; si < d.segs.size(); ++si) {
+        const auto& s = d.segs[si];
+        const ConvSrc& src = d.srcs[s.src];
+        const int chunks = src.C / 64;
+        const int cin = seg_cin_real[si];
+        const int ks = s.ks, kv = ks * ks * ks;
+        const float* w = seg_weights[si];   // [Cout][cin][kd][kh][kw]
+        auto put = [&](int tile, int c, int kd, int kh, int kw) {
+            for (int co = 0; co < d.Cout; ++co)
+                for (int cil = 0; cil < 64; ++cil) {
+                    const int ci = c * 64 + cil;
+                    if (ci >= cin) continue;
+                    const float v = w[((size_t)co * cin + ci) * kv + (kd * ks + kh) * ks + kw];
+                    packed[(size_t)co * K + (size_t)tile * 64 + cil] = __float2half(v);
+                }
+        };
+        if (ks == 1) {
+            for (int c = 0; c < chunks; ++c) put(wtile++, c, 0, 0, 0);
+        } else if (d.stride == 1) {
+            for (int c = 0; c < chunks; ++c)
+                for (int kw = 0; kw < 3; ++kw) {
+                    for (int kd = 0; kd < 3; ++kd)
+                        for (int kh = 0; kh < 3; ++kh) put(wtile + kd * 3 + kh, c, kd, kh, kw);
+                    wtile += 9;
+                }
+        } else {
+            for (int c = 0; c < chunks; ++c)
+                for (int kw = 0; kw < 3; ++kw)
+                    for (int kh = 0; kh < 3; ++kh)
+                        for (int kd = 0; kd < 3; ++kd) put(wtile++, c, kd, kh, kw);
+        }
+    }
+}
+
+// ---- driver entry point for tensor-map encoding (no link-time dependency on libcuda)
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(p);
+    }
+    return fn;
+}
+
+int conv_plan_create(const ConvDesc& d, int* d_err_flag, ConvPlan& plan, char* err, int errlen) {
+    auto fail = [&](const char* m) { snprintf(err, errlen, "conv_plan_create: %s", m); return 1; };
+    PFN_encodeTiled enc = get_encode_fn();
+    if (!enc) return fail("cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+    if (d.srcs.empty() || d.segs.empty()) return fail("no sources/segments");
+    for (const auto& s : d.srcs)
+        if (s.C % 64) return fail("source channels must be a multiple of 64");
+    if (d.Cout_pad % 16 || d.Cout_pad < d.Cout) return fail("Cout_pad must be a multiple of 16 >= Cout");
+
+    ConvKernelParams& p = plan.p;
+    memset(&p, 0, sizeof(p));
+    p.NB = d.NB; p.D = d.D; p.H = d.H; p.W = d.W; p.stride = d.stride;
+    p.TW = (d.W >= 16) ? 16 : 8;
+    p.TH = 128 / p.TW;
+    p.Cout = d.Cout;
+
+    const auto slots = conv_src_slots(d);
+    if ((int)slots.size() > kConvMaxSrc) return fail("too many (source, tap-class) slots");
+    const std::vector<ConvPhase> phases = conv_build_phases(d);
+    p.n_phases = (int)phases.size();
+    int max_taps = 1;
+    bool any3 = false;
+    for (const auto& P : phases) { max_taps = std::max(max_taps, P.n_kh * P.n_kd); any3 |= (P.n_kh == 3); }
+
+    // N tile
+    int bn = d.block_n;
+    if (bn == 0) bn = any3 ? std::min(64, d.Cout_pad) : std::min(256, d.Cout_pad);
+    if (bn % 16 || bn > 256 || bn < 16) return fail("bad block_n");
+    p.block_n = bn;
+    p.n_tiles = (d.Cout_pad + bn - 1) / bn;
+
+    // TD: accumulators per set
+    int td = d.td ? d.td : std::min(4, 512 / (2 * bn));
+    td = std::max(1, std::min(td, d.D));
+    if (!any3) td = std::min(td, 2);    // no plane re-use without kd taps: smaller tiles, more CTAs
+    p.TD = td;
+    p.acc_sets = (2 * td * bn <= 512) ? 2 : 1;
+    if (td * bn > 512) return fail("TD*block_n exceeds TMEM");
+    p.tiles_w = (d.W + p.TW - 1) / p.TW;
+    p.tiles_h = (d.H + p.TH - 1) / p.TH;
+    p.tiles_d = (d.D + p.TD - 1) / p.TD;
+
+    // split-K
+    const int items = d.NB * p.tiles_w * p.tiles_h * p.tiles_d * p.n_tiles;
+    int split = d.split_k;
+    if (split <= 0) {
+        split = 1;
+        while (items * split < 120 && split * 2 <= p.n_phases && split < 64) split *= 2;
+    }
+    split = std::max(1, std::min(split, p.n_phases));
+    p.split_k = split;
+    p.atomic_out = split > 1;
+    plan.needs_zero = split > 1;
+
+    // shared memory plan
+    for (size_t i = 0; i < slots.size(); ++i) p.slab_rows[i] = p.TW * (p.TH + slots[i].n_kh - 1);
+    int max_rows = 0;
+    for (size_t i = 0; i < slots.size(); ++i) max_rows = std::max(max_rows, p.slab_rows[i]);
+    p.w_stage_bytes = max_taps * bn * 128;
+    p.s_stage_bytes = max_rows * 128;
+    const int avail = 227 * 1024 - 2048;   // 1 KB alignment slack + control block
+    p.w_stages = (2 * p.w_stage_bytes + 2 * p.s_stage_bytes <= avail) ? 2 : 1;
+    if (p.w_stages * p.w_stage_bytes + 2 * p.s_stage_bytes > avail) return fail("tile does not fit in shared memory");
+    p.s_stages = std::min(kMaxSStages, (avail - p.w_stages * p.w_stage_bytes) / p.s_stage_bytes);
+    p.s_stages = std::min(p.s_stages, 6);
+    plan.smem_bytes = p.w_stages * p.w_stage_bytes + p.s_stages * p.s_stage_bytes + 2048;
+
+    // tensor maps: activations
+    for (size_t i = 0; i < slots.size(); ++i) {
+        const ConvSrc& s = d.srcs[slots[i].src];
+        cuuint64_t gdim[5] = {(cuuint64_t)s.C, (cuuint64_t)s.Win, (cuuint64_t)s.Hin, (cuuint64_t)s.Din, (cuuint64_t)d.NB};
+        cuuint64_t gstr[4] = {(cuuint64_t)s.C * 2, (cuuint64_t)s.Win * s.C * 2,
+                              (cuuint64_t)s.Hin * s.Win * s.C * 2, (cuuint64_t)s.Din * s.Hin * s.Win * s.C * 2};
+        cuuint32_t box[5] = {64, (cuuint32_t)(p.TW * d.stride), (cuuint32_t)((p.TH + slots[i].n_kh - 1) * d.stride), 1, 1};
+        cuuint32_t estr[5] = {1, (cuuint32_t)d.stride, (cuuint32_t)d.stride, 1, 1};
+        CUresult r = enc(&p.tmA[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, (void*)s.ptr, gdim, gstr, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { snprintf(err, errlen, "cuTensorMapEncodeTiled(A%zu) failed: %d", i, (int)r); return 1; }
+    }
+    for (size_t i = slots.size(); i < (size_t)kConvMaxSrc; ++i) p.tmA[i] = p.tmA[0];
+    {
+        const int K = conv_k_total(d);
+        cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)d.Cout_pad};
+        cuuint64_t gstr[1] = {(cuuint64_t)K * 2};
+        cuuint32_t box[2] = {64, (cuuint32_t)std::min(bn, d.Cout_pad)};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = enc(&p.tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)d.weights, gdim, gstr, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { snprintf(err, errlen, "cuTensorMapEncodeTiled(B) failed: %d", (int)r); return 1; }
+    }
+
+    if (cudaMalloc(&plan.d_phases, phases.size() * sizeof(ConvPhase)) != cudaSuccess) return fail("cudaMalloc phases");
+    cudaMemcpy(plan.d_phases, phases.data(), phases.size() * sizeof(ConvPhase), cudaMemcpyHostToDevice);
+    p.phases = plan.d_phases;
+
+    p.bias = d.bias; p.residual = d.residual; p.out = d.out;
+    p.out_ld = d.out_ld ? d.out_ld : d.Cout; p.out_c0 = d.out_c0; p.out_planar = d.out_planar;
+    p.err_flag = d_err_flag;
+    p.desc_xor = 0;
+    plan.out_bytes = d.out_planar ? (size_t)d.NB * d.Cout * d.D * d.H * d.W * 4
+                                  : (size_t)d.NB * d.D * d.H * d.W * p.out_ld * 4;
+
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    plan.grid = std::min(items * split, sms);
+
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(conv3d_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+            return fail("cudaFuncSetAttribute(max dynamic smem)");
+        attr_set = true;
+    }
+    return 0;
+}
+
+void conv_plan_destroy(ConvPlan& plan) {
+    if (plan.d_phases) cudaFree(plan.d_phases);
+    plan.d_phases = nullptr;
+}
+
+int conv_plan_launch(const ConvPlan& plan, cudaStream_t stream) {
+    if (plan.needs_zero) {
+        // split-K accumulates with red.add: only the channel slice written by this conv may be
+        // cleared when out_ld > Cout, so callers with sliced outputs must not use split-K.
+        cudaMemsetAsync(plan.p.out, 0, plan.out_bytes, stream);
+    }
+    conv3d_igemm_kernel<<<plan.grid, kConvThreads, plan.smem_bytes, stream>>>(plan.p);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace pixie

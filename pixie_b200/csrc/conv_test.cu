@@ -1,0 +1,230 @@
+// Standalone bring-up harness for the tcgen05 implicit-GEMM conv (not part of the product library).
+// Runs a list of small convolutions against a CPU reference and a few large ones for timing.
+//   usage: conv_test [case-filter-substring]
+//   env:   PIXIE_DESC_XOR=<hex>   xor into the high word of every smem descriptor (bring-up only)
+#include "conv3d_igemm.cuh"
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <random>
+#include <string>
+#include <vector>
+
+using namespace pixie;
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(2); } } while (0)
+
+struct Case {
+    std::string name;
+    int NB, Dout, stride;
+    std::vector<int> srcC;                 // channels (padded to 64) per source
+    std::vector<int> srcCreal;
+    std::vector<std::pair<int, int>> segs; // (src, ks)
+    int Cout;
+    bool bias, residual, planar;
+    int split_k, block_n, td;
+    bool timing;
+};
+
+static float frand(std::mt19937& g) { return std::uniform_real_distribution<float>(-1.f, 1.f)(g); }
+
+int main(int argc, char** argv) {
+    const char* filter = argc > 1 ? argv[1] : "";
+    uint64_t hi_xor = 0;
+    if (const char* e = getenv("PIXIE_DESC_XOR")) hi_xor = strtoull(e, nullptr, 16);
+
+    std::vector<Case> cases = {
+        {"gemm1x1_64_64_d16", 1, 16, 1, {64}, {64}, {{0, 1}}, 64, false, false, false, 1, 0, 0, false},
+        {"gemm1x1_128_32_d16", 1, 16, 1, {128}, {128}, {{0, 1}}, 32, true, false, false, 1, 0, 0, false},
+        {"conv3_64_64_d16", 1, 16, 1, {64}, {64}, {{0, 3}}, 64, false, false, false, 1, 0, 0, false},
+        {"conv3_64_64_d16_td1", 1, 16, 1, {64}, {64}, {{0, 3}}, 64, true, false, false, 1, 0, 1, false},
+        {"conv3_32pad_64_d16", 2, 16, 1, {64}, {32}, {{0, 3}}, 64, true, false, false, 1, 0, 0, false},
+        {"conv3_cat_skip_d16", 1, 16, 1, {128, 64, 64}, {128, 64, 64}, {{0, 3}, {1, 1}, {2, 1}}, 64, true, true, false, 1, 0, 0, false},
+        {"conv3_128_128_d16", 1, 16, 1, {128}, {128}, {{0, 3}}, 128, true, true, false, 1, 0, 0, false},
+        {"conv3_256_256_d8_splitk", 1, 8, 1, {256}, {256}, {{0, 3}}, 256, true, true, false, 0, 0, 0, false},
+        {"conv3_s2_64_64_d16to8", 1, 8, 2, {64}, {64}, {{0, 3}}, 64, true, false, false, 1, 0, 0, false},
+        {"conv3_s2_64_64_d32to16", 1, 16, 2, {64}, {64}, {{0, 3}}, 64, true, false, false, 1, 0, 0, false},
+        {"head_64_3_planar_d16", 1, 16, 1, {64}, {64}, {{0, 3}}, 3, true, false, true, 1, 0, 0, false},
+        {"qkv_256_768_d8", 1, 8, 1, {256}, {256}, {{0, 1}}, 768, true, false, false, 1, 0, 0, false},
+        {"conv3_256_256_d4", 1, 4, 1, {256}, {256}, {{0, 3}}, 256, true, false, false, 0, 0, 0, false},
+        {"T_conv3_64_64_d64", 1, 64, 1, {64}, {64}, {{0, 3}}, 64, true, false, false, 1, 0, 0, true},
+        {"T_conv3_64_64_d64_td2", 1, 64, 1, {64}, {64}, {{0, 3}}, 64, true, false, false, 1, 0, 2, true},
+        {"T_conv3_128_64_d64", 1, 64, 1, {128}, {128}, {{0, 3}}, 64, true, true, false, 1, 0, 0, true},
+        {"T_conv3_128_128_d64", 1, 64, 1, {128}, {128}, {{0, 3}}, 128, true, false, false, 1, 0, 0, true},
+        {"T_conv3_128_128_d64_bn128", 1, 64, 1, {128}, {128}, {{0, 3}}, 128, true, false, false, 1, 128, 0, true},
+        {"T_gemm1x1_512_128_d64", 1, 64, 1, {512}, {512}, {{0, 1}}, 128, true, false, false, 1, 0, 0, true},
+        {"T_conv3_64_64_d32", 1, 32, 1, {64}, {64}, {{0, 3}}, 64, true, false, false, 1, 0, 0, true},
+        {"T_conv3_256_256_d8", 1, 8, 1, {256}, {256}, {{0, 3}}, 256, true, false, false, 0, 0, 0, true},
+        {"T_conv3_128_128_d16", 1, 16, 1, {128}, {128}, {{0, 3}}, 128, true, false, false, 0, 0, 0, true},
+    };
+
+    int* d_err = nullptr;
+    CK(cudaMalloc(&d_err, sizeof(int)));
+    int n_fail = 0, n_run = 0;
+
+    for (const Case& c : cases) {
+        if (filter[0] && c.name.find(filter) == std::string::npos) continue;
+        ++n_run;
+        std::mt19937 gen(1234);
+        const int Do = c.Dout, Di = c.Dout * c.stride;
+        const size_t vox_in = (size_t)c.NB * Di * Di * Di, vox_out = (size_t)c.NB * Do * Do * Do;
+
+        ConvDesc d;
+        d.NB = c.NB; d.D = d.H = d.W = Do; d.stride = c.stride; d.Cout = c.Cout;
+        d.Cout_pad = (c.Cout + 15) / 16 * 16;
+        d.split_k = c.split_k; d.block_n = c.block_n; d.td = c.td; d.out_planar = c.planar;
+
+        std::vector<std::vector<__half>> h_src(c.srcC.size());
+        std::vector<__half*> d_src(c.srcC.size());
+        for (size_t s = 0; s < c.srcC.size(); ++s) {
+            h_src[s].resize(vox_in * c.srcC[s]);
+            for (size_t v = 0; v < vox_in; ++v)
+                for (int ch = 0; ch < c.srcC[s]; ++ch)
+                    h_src[s][v * c.srcC[s] + ch] = __float2half(ch < c.srcCreal[s] ? frand(gen) : 0.f);
+            CK(cudaMalloc(&d_src[s], h_src[s].size() * 2));
+            CK(cudaMemcpy(d_src[s], h_src[s].data(), h_src[s].size() * 2, cudaMemcpyHostToDevice));
+            d.srcs.push_back({d_src[s], c.srcC[s], Di, Di, Di});
+        }
+        std::vector<std::vector<float>> h_w(c.segs.size());
+        std::vector<const float*> wptr;
+        std::vector<int> cin_real;
+        for (size_t g = 0; g < c.segs.size(); ++g) {
+            const int src = c.segs[g].first, ks = c.segs[g].second;
+            d.segs.push_back({src, ks});
+            const int cin = c.srcCreal[src];
+            h_w[g].resize((size_t)c.Cout * cin * ks * ks * ks);
+            const float sc = 1.0f / std::sqrt((float)cin * ks * ks * ks);
+            for (auto& x : h_w[g]) x = __half2float(__float2half(frand(gen) * sc));
+            wptr.push_back(h_w[g].data());
+            cin_real.push_back(cin);
+        }
+        std::vector<__half> packed;
+        conv_pack_weights(d, wptr, cin_real, packed);
+        __half* d_w;
+        CK(cudaMalloc(&d_w, packed.size() * 2));
+        CK(cudaMemcpy(d_w, packed.data(), packed.size() * 2, cudaMemcpyHostToDevice));
+        d.weights = d_w;
+
+        std::vector<float> h_bias(c.Cout), h_res;
+        float *d_bias = nullptr, *d_res = nullptr, *d_out = nullptr;
+        for (auto& x : h_bias) x = frand(gen);
+        if (c.bias) {
+            CK(cudaMalloc(&d_bias, c.Cout * 4));
+            CK(cudaMemcpy(d_bias, h_bias.data(), c.Cout * 4, cudaMemcpyHostToDevice));
+            d.bias = d_bias;
+        }
+        const size_t out_elems = vox_out * c.Cout;
+        if (c.residual) {
+            h_res.resize(out_elems);
+            for (auto& x : h_res) x = frand(gen);
+            CK(cudaMalloc(&d_res, out_elems * 4));
+            CK(cudaMemcpy(d_res, h_res.data(), out_elems * 4, cudaMemcpyHostToDevice));
+            d.residual = d_res;
+        }
+        CK(cudaMalloc(&d_out, out_elems * 4));
+        CK(cudaMemset(d_out, 0xFF, out_elems * 4));   // NaN pattern: unwritten outputs are caught
+        d.out = d_out; d.out_ld = c.Cout;
+
+        CK(cudaMemset(d_err, 0, sizeof(int)));
+        ConvPlan plan;
+        char err[256] = {0};
+        if (conv_plan_create(d, d_err, plan, err, sizeof(err))) {
+            printf("[%s] PLAN FAILED: %s\n", c.name.c_str(), err);
+            ++n_fail;
+            continue;
+        }
+        plan.p.desc_xor = hi_xor;
+        printf("[%s] grid=%d smem=%d bn=%d TD=%d TW=%d TH=%d acc_sets=%d w_stages=%d s_stages=%d phases=%d split=%d\n",
+               c.name.c_str(), plan.grid, plan.smem_bytes, plan.p.block_n, plan.p.TD, plan.p.TW, plan.p.TH,
+               plan.p.acc_sets, plan.p.w_stages, plan.p.s_stages, plan.p.n_phases, plan.p.split_k);
+        fflush(stdout);
+
+        int lrc = conv_plan_launch(plan, 0);
+        cudaError_t se = cudaDeviceSynchronize();
+        int h_err = 0;
+        cudaMemcpy(&h_err, d_err, sizeof(int), cudaMemcpyDeviceToHost);
+        if (lrc || se != cudaSuccess || h_err) {
+            printf("[%s] LAUNCH FAILED: launch=%d sync=%s pipeline_timeout_flag=%d\n", c.name.c_str(), lrc,
+                   cudaGetErrorString(se), h_err);
+            ++n_fail;
+            if (se != cudaSuccess) { printf("sticky CUDA error, stopping\n"); return 3; }
+            continue;
+        }
+
+        if (c.timing) {
+            cudaEvent_t e0, e1;
+            cudaEventCreate(&e0); cudaEventCreate(&e1);
+            for (int i = 0; i < 3; ++i) conv_plan_launch(plan, 0);
+            cudaEventRecord(e0);
+            const int iters = 20;
+            for (int i = 0; i < iters; ++i) conv_plan_launch(plan, 0);
+            cudaEventRecord(e1);
+            CK(cudaEventSynchronize(e1));
+            float ms = 0;
+            cudaEventElapsedTime(&ms, e0, e1);
+            ms /= iters;
+            double flops = 2.0 * vox_out * c.Cout * (double)conv_k_total(d);
+            printf("[%s] TIME %.3f ms  %.1f TFLOP/s (padded-K flops)\n", c.name.c_str(), ms, flops / ms * 1e-9);
+        }
+
+        // verification (sampled voxels for big cases)
+        std::vector<float> h_out(out_elems);
+        CK(cudaMemcpy(h_out.data(), d_out, out_elems * 4, cudaMemcpyDeviceToHost));
+        const size_t nsample = c.timing ? 600 : vox_out;
+        double max_err = 0, max_ref = 0;
+        size_t bad = 0, nan_cnt = 0;
+        std::mt19937 g2(99);
+        for (size_t si = 0; si < nsample; ++si) {
+            size_t v = c.timing ? (size_t)(std::uniform_int_distribution<size_t>(0, vox_out - 1)(g2)) : si;
+            if (c.timing && si < 64) v = si * (vox_out / 64);   // include structured positions (corners/edges)
+            size_t t = v;
+            const int ow = t % Do; t /= Do;
+            const int oh = t % Do; t /= Do;
+            const int od = t % Do; t /= Do;
+            const int nb = (int)t;
+            for (int co = 0; co < c.Cout; ++co) {
+                double acc = c.bias ? h_bias[co] : 0.0;
+                for (size_t g = 0; g < c.segs.size(); ++g) {
+                    const int src = c.segs[g].first, ks = c.segs[g].second, pad = ks / 2;
+                    const int cin = c.srcCreal[src], C = c.srcC[src];
+                    for (int kd = 0; kd < ks; ++kd)
+                        for (int kh = 0; kh < ks; ++kh)
+                            for (int kw = 0; kw < ks; ++kw) {
+                                const int id = od * c.stride + kd - pad, ih = oh * c.stride + kh - pad, iw = ow * c.stride + kw - pad;
+                                if (ks == 1) { /* 1x1 convs always read the same-resolution voxel */ }
+                                if (id < 0 || ih < 0 || iw < 0 || id >= Di || ih >= Di || iw >= Di) continue;
+                                const __half* xp = &h_src[src][((((size_t)nb * Di + id) * Di + ih) * Di + iw) * C];
+                                const float* wp = &h_w[g][(size_t)co * cin * ks * ks * ks + (kd * ks + kh) * ks + kw];
+                                for (int ci = 0; ci < cin; ++ci)
+                                    acc += (double)__half2float(xp[ci]) * wp[(size_t)ci * ks * ks * ks];
+                            }
+                }
+                const size_t oidx_nd = v * c.Cout + co;
+                if (c.residual) acc += h_res[oidx_nd];
+                const size_t oidx = c.planar ? ((size_t)nb * c.Cout + co) * ((size_t)Do * Do * Do) + (v % ((size_t)Do * Do * Do)) : oidx_nd;
+                const float got = h_out[oidx];
+                if (std::isnan(got)) { ++nan_cnt; continue; }
+                const double e = std::fabs(got - acc);
+                max_err = std::max(max_err, e);
+                max_ref = std::max(max_ref, std::fabs(acc));
+                if (e > 2e-3 * std::max(1.0, std::fabs(acc))) ++bad;
+            }
+        }
+        const bool pass = (bad == 0 && nan_cnt == 0);
+        printf("[%s] %s max_err=%.3e max_ref=%.3f bad=%zu nan=%zu\n", c.name.c_str(), pass ? "PASS" : "FAIL", max_err, max_ref, bad, nan_cnt);
+        if (!pass) {
+            ++n_fail;
+            // print a few values to help diagnose layout errors
+            for (int i = 0; i < 8 && i < (int)out_elems; ++i) printf("   out[%d]=%g\n", i, h_out[i]);
+        }
+        fflush(stdout);
+
+        conv_plan_destroy(plan);
+        for (auto p : d_src) cudaFree(p);
+        cudaFree(d_w); cudaFree(d_bias); cudaFree(d_res); cudaFree(d_out);
+    }
+    printf("SUMMARY run=%d fail=%d\n", n_run, n_fail);
+    return n_fail ? 1 : 0;
+}
