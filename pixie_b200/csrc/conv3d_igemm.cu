@@ -359,7 +359,8 @@ void conv_pack_weights(const ConvDesc& d, const std::vector<const float*>& seg_w
                 for (int cil = 0; cil < 64; ++cil) {
                     const int ci = c * 64 + cil;
                     if (ci >= cin) continue;
-                    const float v = w[((size_t)co * cin + ci) * kv + (kd * ks + kh) * ks + kw];
+                    float v = w[((size_t)co * cin + ci) * kv + (kd * ks + kh) * ks + kw];
+                    if (s.wlo) v = v - __half2float(__float2half(v));
                     packed[(size_t)co * K + (size_t)tile * 64 + cil] = __float2half(v);
                 }
         };
@@ -397,6 +398,31 @@ static PFN_encodeTiled get_encode_fn() {
             fn = reinterpret_cast<PFN_encodeTiled>(p);
     }
     return fn;
+}
+
+
+static int encode_a_maps(const ConvDesc& d, ConvKernelParams& p, PFN_encodeTiled enc, char* err, int errlen) {
+    const auto slots = conv_src_slots(d);
+    for (size_t i = 0; i < slots.size(); ++i) {
+        const ConvSrc& s = d.srcs[slots[i].src];
+        cuuint64_t gdim[5] = {(cuuint64_t)s.C, (cuuint64_t)s.Win, (cuuint64_t)s.Hin, (cuuint64_t)s.Din, (cuuint64_t)d.NB};
+        cuuint64_t gstr[4] = {(cuuint64_t)s.C * 2, (cuuint64_t)s.Win * s.C * 2,
+                              (cuuint64_t)s.Hin * s.Win * s.C * 2, (cuuint64_t)s.Din * s.Hin * s.Win * s.C * 2};
+        cuuint32_t box[5] = {64, (cuuint32_t)(p.TW * d.stride), (cuuint32_t)((p.TH + slots[i].n_kh - 1) * d.stride), 1, 1};
+        cuuint32_t estr[5] = {1, (cuuint32_t)d.stride, (cuuint32_t)d.stride, 1, 1};
+        CUresult r = enc(&p.tmA[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, (void*)s.ptr, gdim, gstr, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { snprintf(err, errlen, "cuTensorMapEncodeTiled(A%zu) failed: %d", i, (int)r); return 1; }
+    }
+    for (size_t i = slots.size(); i < (size_t)kConvMaxSrc; ++i) p.tmA[i] = p.tmA[0];
+    return 0;
+}
+
+int conv_plan_retarget(const ConvDesc& d, ConvPlan& plan, char* err, int errlen) {
+    PFN_encodeTiled enc = get_encode_fn();
+    if (!enc) { snprintf(err, errlen, "cuTensorMapEncodeTiled unavailable"); return 1; }
+    return encode_a_maps(d, plan.p, enc, err, errlen);
 }
 
 int conv_plan_create(const ConvDesc& d, int* d_err_flag, ConvPlan& plan, char* err, int errlen) {
@@ -466,20 +492,7 @@ int conv_plan_create(const ConvDesc& d, int* d_err_flag, ConvPlan& plan, char* e
     p.s_stages = std::min(p.s_stages, 6);
     plan.smem_bytes = p.w_stages * p.w_stage_bytes + p.s_stages * p.s_stage_bytes + 2048;
 
-    // tensor maps: activations
-    for (size_t i = 0; i < slots.size(); ++i) {
-        const ConvSrc& s = d.srcs[slots[i].src];
-        cuuint64_t gdim[5] = {(cuuint64_t)s.C, (cuuint64_t)s.Win, (cuuint64_t)s.Hin, (cuuint64_t)s.Din, (cuuint64_t)d.NB};
-        cuuint64_t gstr[4] = {(cuuint64_t)s.C * 2, (cuuint64_t)s.Win * s.C * 2,
-                              (cuuint64_t)s.Hin * s.Win * s.C * 2, (cuuint64_t)s.Din * s.Hin * s.Win * s.C * 2};
-        cuuint32_t box[5] = {64, (cuuint32_t)(p.TW * d.stride), (cuuint32_t)((p.TH + slots[i].n_kh - 1) * d.stride), 1, 1};
-        cuuint32_t estr[5] = {1, (cuuint32_t)d.stride, (cuuint32_t)d.stride, 1, 1};
-        CUresult r = enc(&p.tmA[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, (void*)s.ptr, gdim, gstr, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) { snprintf(err, errlen, "cuTensorMapEncodeTiled(A%zu) failed: %d", i, (int)r); return 1; }
-    }
-    for (size_t i = slots.size(); i < (size_t)kConvMaxSrc; ++i) p.tmA[i] = p.tmA[0];
+    if (encode_a_maps(d, p, enc, err, errlen)) return 1;
     {
         const int K = conv_k_total(d);
         cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)d.Cout_pad};

@@ -29,7 +29,7 @@
 
 namespace pixie {
 
-constexpr int kConvMaxSrc = 4;
+constexpr int kConvMaxSrc = 8;
 constexpr int kConvThreads = 192;  // warp0 TMA, warp1 MMA, warps2-5 epilogue
 
 struct ConvPhase {        // 16 bytes, lives in global memory
@@ -90,7 +90,8 @@ struct ConvDesc {
     int stride = 1;
     int Cout = 0;
     // K segments: each segment is (source, kernel size 1 or 3) over all of the source's channels.
-    struct Seg { int src; int ks; };
+    // wlo = 1 packs the fp16 rounding residual of the weights (w - fp16(w)) for split-precision mode.
+    struct Seg { int src; int ks; int wlo = 0; };
     std::vector<ConvSrc> srcs;
     std::vector<Seg> segs;
     const __half* weights = nullptr;   // packed by pack_conv_weights(), [Cout_pad][K_total]
@@ -129,5 +130,6 @@ struct ConvPlan {
 int conv_plan_create(const ConvDesc& d, int* d_err_flag, ConvPlan& plan, char* err, int errlen);
 void conv_plan_destroy(ConvPlan& plan);
 int conv_plan_launch(const ConvPlan& plan, cudaStream_t stream);
-// Re-point the data pointers of a prepared plan (tensor maps are re-encoded).
+// Re-encode the activation tensor maps after the source pointers in `d` changed (same shapes).
+int conv_plan_retarget(const ConvDesc& d, ConvPlan& plan, char* err, int errlen);
 }  // namespace pixie

@@ -1,0 +1,667 @@
+// MLS-MPM / APIC substep for sm_100a.  Replaces MPM_Simulator_WARP.p2g2p
+// (third_party/PhysGaussian/mpm_solver_warp/mpm_solver_warp.py:514-637) and the Warp kernels it
+// launches (mpm_utils.py:295-588, BC closures mpm_solver_warp.py:785-1179).
+//
+// One substep = three launches, no host synchronisation:
+//   mpm_p2g   : [impulse / Dirichlet particle BCs] -> return mapping + Kirchhoff stress -> scatter
+//               (one red.global.add.v4.f32 per node: grid node = float4 {mv.xyz, m})
+//   mpm_grid  : normalise + gravity + damping + every grid BC (from a device BC table, registration
+//               order) -> grid_v; clears the {mv, m} node it just consumed (zero_grid fused away)
+//   mpm_g2p   : gather, x/v/C/F_trial update, optional covariance update; thread 0 advances the
+//               simulation clock and moves the cuboid colliders (the reference's host-side
+//               `modify`, mpm_solver_warp.py:899-905, and `self.time += dt`, :637)
+// Substeps are replayed from a CUDA graph.
+#include "mpm.cuh"
+#include "mpm_math.cuh"
+#include "ptx.cuh"
+
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+namespace pixie {
+
+using namespace mpm;
+
+namespace {
+
+constexpr int kMaxBC = 96;     // release_particles_sequentially registers 50 modifiers on its own
+
+struct DevBC {
+    int kind;
+    float point[3], normal[3], size[3], velocity[3];
+    float start_time, end_time, friction;
+    int surface_type, reset;
+    float h1[3], h2[3], hhr[2];
+    float rotation_scale, translation_scale;
+    const int* mask;
+};
+
+struct DevState {
+    // particles
+    float *x, *v, *F, *F_trial, *C, *stress, *R, *cov, *init_cov;
+    float *vol, *mass, *density, *E, *nu, *mu, *lam, *bulk, *yield_stress;
+    int *material, *selection;
+    // grid
+    float4* grid_mv;    // {momentum.xyz, mass}
+    float4* grid_v;     // {velocity.xyz, 0}
+    // clock + BCs
+    double* time;
+    DevBC* bcs;
+    int n_bc;
+    // scalars
+    int n, n_grid;
+    float dx, inv_dx;
+    float gx, gy, gz;
+    float rpic_damping, grid_v_damping_scale, alpha, hardening, xi, plastic_viscosity, softening;
+    int update_cov_with_F;
+};
+
+__device__ __forceinline__ M3 load_m3(const float* p, int i) {
+    M3 a;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) a.m[k] = p[(size_t)i * 9 + k];
+    return a;
+}
+__device__ __forceinline__ void store_m3(float* p, int i, const M3& a) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) p[(size_t)i * 9 + k] = a.m[k];
+}
+
+struct Weights { int bx, by, bz; float fx[3]; float w[3][3]; float dw[3][3]; };   // [axis][node]
+
+__device__ __forceinline__ Weights bspline(const DevState& s, float px, float py, float pz) {
+    Weights W;
+    const float g[3] = {px * s.inv_dx, py * s.inv_dx, pz * s.inv_dx};
+    int b[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        b[a] = (int)(g[a] - 0.5f);                      // wp.int truncates toward zero (mpm_utils.py:344-346)
+        const float fx = g[a] - (float)b[a];
+        W.fx[a] = fx;
+        const float wa = 1.5f - fx, wb = fx - 1.0f, wc = fx - 0.5f;
+        W.w[a][0] = wa * wa * 0.5f;
+        W.w[a][1] = 0.f - wb * wb + 0.75f;
+        W.w[a][2] = wc * wc * 0.5f;
+        W.dw[a][0] = fx - 1.5f;
+        W.dw[a][1] = -2.0f * (fx - 1.0f);
+        W.dw[a][2] = fx - 0.5f;
+    }
+    W.bx = b[0]; W.by = b[1]; W.bz = b[2];
+    return W;
+}
+
+// ------------------------------------------------------------------------------------------ p2g
+__global__ void __launch_bounds__(128)
+mpm_p2g_kernel(const DevState s, const float dt) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= s.n) return;
+    const float time = (float)(*s.time);
+    float vx = s.v[3 * p], vy = s.v[3 * p + 1], vz = s.v[3 * p + 2];
+    const float px = s.x[3 * p], py = s.x[3 * p + 1], pz = s.x[3 * p + 2];
+    const float mass = s.mass[p];
+
+    // ---- pre-p2g particle operations: all impulses first, then all velocity modifiers
+    //      (mpm_solver_warp.py:528-547)
+    bool v_dirty = false;
+    for (int k = 0; k < s.n_bc; ++k) {
+        const DevBC& bc = s.bcs[k];
+        if (bc.kind != PIXIE_BC_IMPULSE) continue;
+        if (time >= bc.start_time && time < bc.end_time && bc.mask[p] == 1) {
+            vx = vx + (bc.velocity[0] / mass) * dt;      // apply_force :1015-1027 (force stored in velocity[])
+            vy = vy + (bc.velocity[1] / mass) * dt;
+            vz = vz + (bc.velocity[2] / mass) * dt;
+            v_dirty = true;
+        }
+    }
+    for (int k = 0; k < s.n_bc; ++k) {
+        const DevBC& bc = s.bcs[k];
+        if (bc.kind == PIXIE_BC_VELOCITY_TRANSLATION) {
+            if (time >= bc.start_time && time < bc.end_time && bc.mask[p] == 1) {
+                vx = bc.velocity[0]; vy = bc.velocity[1]; vz = bc.velocity[2];
+                v_dirty = true;
+            }
+        } else if (bc.kind == PIXIE_BC_VELOCITY_ROTATION) {
+            if (time >= bc.start_time && time < bc.end_time && bc.mask[p] == 1) {
+                // modify_particle_v_before_p2g :1137-1179
+                const float ox = px - bc.point[0], oy = py - bc.point[1], oz = pz - bc.point[2];
+                const float on = ox * bc.normal[0] + oy * bc.normal[1] + oz * bc.normal[2];
+                const float hx = ox - on * bc.normal[0], hy = oy - on * bc.normal[1], hz = oz - on * bc.normal[2];
+                const float hd = sqrtf(hx * hx + hy * hy + hz * hz);
+                const float cosine = (ox * bc.h1[0] + oy * bc.h1[1] + oz * bc.h1[2]) / hd;
+                float theta = acosf(cosine);
+                if (!(ox * bc.h2[0] + oy * bc.h2[1] + oz * bc.h2[2] > 0.f)) theta = -theta;
+                const float a1 = -hd * sinf(theta) * bc.rotation_scale;
+                const float a2 = hd * cosf(theta) * bc.rotation_scale;
+                const float av = bc.translation_scale;
+                vx = a1 * bc.h1[0] + a2 * bc.h2[0] + av * bc.normal[0];
+                vy = a1 * bc.h1[1] + a2 * bc.h2[1] + av * bc.normal[1];
+                vz = a1 * bc.h1[2] + a2 * bc.h2[2] + av * bc.normal[2];
+                v_dirty = true;
+            }
+        }
+    }
+    if (v_dirty) { s.v[3 * p] = vx; s.v[3 * p + 1] = vy; s.v[3 * p + 2] = vz; }
+
+    if (s.selection[p] != 0) return;
+
+    // ---- compute_stress_from_F_trial (mpm_utils.py:467-526)
+    const int material = s.material[p];
+    float mu = s.mu[p], lam = s.lam[p];
+    const M3 Ft = load_m3(s.F_trial, p);
+    M3 F = Ft;
+    if (material == 1) {
+        float ys = s.yield_stress[p];
+        const float ys0 = ys;
+        F = return_von_mises(Ft, mu, lam, ys, s.hardening, s.xi, false, 0.f, mu, lam);
+        if (ys != ys0) s.yield_stress[p] = ys;
+    } else if (material == 2) {
+        F = return_sand(Ft, mu, lam, s.alpha);
+    } else if (material == 3) {
+        F = return_viscoplastic(Ft, mu, s.yield_stress[p], s.plastic_viscosity, dt);
+    } else if (material == 5) {
+        float ys = s.yield_stress[p];
+        const float ys0 = ys, mu0 = mu;
+        F = return_von_mises(Ft, mu, lam, ys, s.hardening, s.xi, true, s.softening, mu, lam);
+        if (ys != ys0) s.yield_stress[p] = ys;
+        if (mu != mu0) { s.mu[p] = mu; s.lam[p] = lam; }
+    }
+    store_m3(s.F, p, F);
+    const float J = m3_det(F);
+    M3 tau = m3_zero();
+    if (material == 6) {
+        tau = stress_water(J, s.bulk[p]);
+    } else if (material != 4 && material >= 0 && material <= 5) {
+        M3 U, V; V3 sig;
+        svd3(F, U, sig, V);
+        if (material == 0 || material == 5) tau = stress_fcr(F, U, V, J, mu, lam);
+        else if (material == 1 || material == 3) tau = stress_stvk(F, U, V, sig, mu, lam);
+        else if (material == 2) tau = stress_drucker_prager(F, U, V, sig, mu, lam);
+    }
+    {   // enforce symmetry
+        const M3 tt = m3_t(tau);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) tau.m[i] = (tau.m[i] + tt.m[i]) / 2.0f;
+    }
+    store_m3(s.stress, p, tau);
+
+    // ---- p2g_apic_with_stress (mpm_utils.py:338-394)
+    const Weights W = bspline(s, px, py, pz);
+    M3 C = load_m3(s.C, p);
+    {
+        const float r = s.rpic_damping;
+        const M3 Ct = m3_t(C);
+        M3 Cn;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) Cn.m[i] = (1.0f - r) * C.m[i] + r / 2.0f * (C.m[i] - Ct.m[i]);
+        C = (r < -0.001f) ? m3_zero() : Cn;
+    }
+    const float vol = s.vol[p];
+    const int n = s.n_grid;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const int ix = W.bx + i, iy = W.by + j, iz = W.bz + k;
+                if ((unsigned)ix >= (unsigned)n || (unsigned)iy >= (unsigned)n || (unsigned)iz >= (unsigned)n)
+                    continue;   // the reference indexes out of bounds here (no checks); we drop the node
+                const V3 dpos = {((float)i - W.fx[0]) * s.dx, ((float)j - W.fx[1]) * s.dx, ((float)k - W.fx[2]) * s.dx};
+                const float weight = W.w[0][i] * W.w[1][j] * W.w[2][k];
+                const V3 dweight = {W.dw[0][i] * W.w[1][j] * W.w[2][k] * s.inv_dx,
+                                    W.w[0][i] * W.dw[1][j] * W.w[2][k] * s.inv_dx,
+                                    W.w[0][i] * W.w[1][j] * W.dw[2][k] * s.inv_dx};
+                const V3 sd = m3_mulv(tau, dweight);
+                const V3 cd = m3_mulv(C, dpos);
+                const float wm = weight * mass;
+                const float ax = wm * (vx + cd.x) + dt * (-vol * sd.x);
+                const float ay = wm * (vy + cd.y) + dt * (-vol * sd.y);
+                const float az = wm * (vz + cd.z) + dt * (-vol * sd.z);
+                float* node = reinterpret_cast<float*>(s.grid_mv + ((size_t)ix * n + iy) * n + iz);
+                ptx::red_add_v4(node, ax, ay, az, wm);
+            }
+}
+
+// ------------------------------------------------------------------------------------------ grid
+__global__ void __launch_bounds__(256)
+mpm_grid_kernel(const DevState s, const float dt) {
+    const int n = s.n_grid;
+    const size_t total = (size_t)n * n * n;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int gz = (int)(idx % n), gy = (int)((idx / n) % n), gx = (int)(idx / ((size_t)n * n));
+    const float time = (float)(*s.time);
+    const float4 mv = s.grid_mv[idx];
+    float vx = 0.f, vy = 0.f, vz = 0.f;
+    if (mv.w > 1e-15f) {                                   // grid_normalization_and_gravity :398-409
+        const float inv = 1.0f / mv.w;
+        vx = mv.x * inv + dt * s.gx;
+        vy = mv.y * inv + dt * s.gy;
+        vz = mv.z * inv + dt * s.gz;
+    }
+    if (s.grid_v_damping_scale < 1.0f) {                   // add_damping_via_grid :583-588 (only if < 1)
+        vx *= s.grid_v_damping_scale; vy *= s.grid_v_damping_scale; vz *= s.grid_v_damping_scale;
+    }
+    for (int k = 0; k < s.n_bc; ++k) {
+        const DevBC& bc = s.bcs[k];
+        const bool active = time >= bc.start_time && time < bc.end_time;
+        if (bc.kind == PIXIE_BC_SURFACE_COLLIDER) {        // :785-840
+            if (active) {
+                const float ox = (float)gx * s.dx - bc.point[0], oy = (float)gy * s.dx - bc.point[1], oz = (float)gz * s.dx - bc.point[2];
+                const float dotp = ox * bc.normal[0] + oy * bc.normal[1] + oz * bc.normal[2];
+                if (dotp < 0.0f) {
+                    if (bc.surface_type == 11) {
+                        const float zz = (float)gz * s.dx;
+                        if (zz < 0.4f || zz > 0.53f) { vx = 0.f; vy = 0.f; vz = 0.f; }
+                        else { vx = vx * 0.3f; vy = 0.0f * 0.3f; vz = vz * 0.3f; }
+                    } else {
+                        // sticky -> 0; slip / separate: the reference computes the projected velocity and
+                        // then overwrites the node with zero (:838-840)
+                        vx = 0.f; vy = 0.f; vz = 0.f;
+                    }
+                }
+            }
+        } else if (bc.kind == PIXIE_BC_CUBOID) {           // :874-897
+            if (active) {
+                const float ox = (float)gx * s.dx - bc.point[0], oy = (float)gy * s.dx - bc.point[1], oz = (float)gz * s.dx - bc.point[2];
+                if (fabsf(ox) < bc.size[0] && fabsf(oy) < bc.size[1] && fabsf(oz) < bc.size[2]) {
+                    vx = bc.velocity[0]; vy = bc.velocity[1]; vz = bc.velocity[2];
+                }
+            } else if (bc.reset == 1) {
+                if (time < bc.end_time + 15.0f * dt) { vx = 0.f; vy = 0.f; vz = 0.f; }
+            }
+        } else if (bc.kind == PIXIE_BC_BOUNDING_BOX) {     // :917-974
+            if (active) {
+                const int padding = 3;
+                if (gx < padding && vx < 0.f) vx = 0.f;
+                if (gx >= n - padding && vx > 0.f) vx = 0.f;
+                if (gy < padding && vy < 0.f) vy = 0.f;
+                if (gy >= n - padding && vy > 0.f) vy = 0.f;
+                if (gz < padding && vz < 0.f) vz = 0.f;
+                if (gz >= n - padding && vz > 0.f) vz = 0.f;
+            }
+        }
+    }
+    s.grid_v[idx] = make_float4(vx, vy, vz, 0.f);
+    if (mv.x != 0.f || mv.y != 0.f || mv.z != 0.f || mv.w != 0.f) s.grid_mv[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+// ------------------------------------------------------------------------------------------ g2p
+__global__ void __launch_bounds__(128)
+mpm_g2p_kernel(const DevState s, const float dt, const double dt_d) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < s.n && s.selection[p] == 0) {
+        const float px = s.x[3 * p], py = s.x[3 * p + 1], pz = s.x[3 * p + 2];
+        const Weights W = bspline(s, px, py, pz);
+        const int n = s.n_grid;
+        float nvx = 0.f, nvy = 0.f, nvz = 0.f;
+        M3 nC = m3_zero(), nF = m3_zero();
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const int ix = W.bx + i, iy = W.by + j, iz = W.bz + k;
+                    float4 gv = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if ((unsigned)ix < (unsigned)n && (unsigned)iy < (unsigned)n && (unsigned)iz < (unsigned)n)
+                        gv = s.grid_v[((size_t)ix * n + iy) * n + iz];
+                    const float dp[3] = {(float)i - W.fx[0], (float)j - W.fx[1], (float)k - W.fx[2]};
+                    const float weight = W.w[0][i] * W.w[1][j] * W.w[2][k];
+                    const float dwv[3] = {W.dw[0][i] * W.w[1][j] * W.w[2][k] * s.inv_dx,
+                                          W.w[0][i] * W.dw[1][j] * W.w[2][k] * s.inv_dx,
+                                          W.w[0][i] * W.w[1][j] * W.dw[2][k] * s.inv_dx};
+                    nvx = nvx + gv.x * weight; nvy = nvy + gv.y * weight; nvz = nvz + gv.z * weight;
+                    const float cw = weight * s.inv_dx * 4.0f;
+                    const float g3[3] = {gv.x, gv.y, gv.z};
+#pragma unroll
+                    for (int r = 0; r < 3; ++r)
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            nC.m[3 * r + c] = nC.m[3 * r + c] + (g3[r] * dp[c]) * cw;
+                            nF.m[3 * r + c] = nF.m[3 * r + c] + g3[r] * dwv[c];
+                        }
+                }
+        s.v[3 * p] = nvx; s.v[3 * p + 1] = nvy; s.v[3 * p + 2] = nvz;
+        s.x[3 * p] = px + dt * nvx; s.x[3 * p + 1] = py + dt * nvy; s.x[3 * p + 2] = pz + dt * nvz;
+        store_m3(s.C, p, nC);
+        M3 A = m3_ident();
+#pragma unroll
+        for (int i = 0; i < 9; ++i) A.m[i] += nF.m[i] * dt;
+        store_m3(s.F_trial, p, m3_mul(A, load_m3(s.F, p)));
+        if (s.update_cov_with_F) {                          // update_cov :315-335
+            float* cv = s.cov + (size_t)p * 6;
+            M3 cn;
+            cn.m[0] = cv[0]; cn.m[1] = cv[1]; cn.m[2] = cv[2]; cn.m[3] = cv[1]; cn.m[4] = cv[3]; cn.m[5] = cv[4];
+            cn.m[6] = cv[2]; cn.m[7] = cv[4]; cn.m[8] = cv[5];
+            const M3 a = m3_mul(nF, cn), b = m3_mul_t(cn, nF);
+            M3 c1;
+#pragma unroll
+            for (int i = 0; i < 9; ++i) c1.m[i] = cn.m[i] + dt * (a.m[i] + b.m[i]);
+            cv[0] = c1.m[0]; cv[1] = c1.m[1]; cv[2] = c1.m[2]; cv[3] = c1.m[4]; cv[4] = c1.m[5]; cv[5] = c1.m[8];
+        }
+    }
+    // ---- substep epilogue: nothing in this kernel reads the clock or the BC table
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const double t = *s.time;
+        for (int k = 0; k < s.n_bc; ++k) {
+            DevBC& bc = s.bcs[k];
+            if (bc.kind == PIXIE_BC_CUBOID && t >= (double)bc.start_time && t < (double)bc.end_time) {
+                // modify(): Python-float arithmetic, stored back as fp32 (mpm_solver_warp.py:899-905)
+                bc.point[0] = (float)((double)bc.point[0] + dt_d * (double)bc.velocity[0]);
+                bc.point[1] = (float)((double)bc.point[1] + dt_d * (double)bc.velocity[1]);
+                bc.point[2] = (float)((double)bc.point[2] + dt_d * (double)bc.velocity[2]);
+            }
+        }
+        *s.time = t + dt_d;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ setup kernels
+__global__ void mpm_mu_lam_kernel(const DevState s) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= s.n) return;
+    const float E = s.E[p], nu = s.nu[p];
+    s.mu[p] = E / (2.0f * (1.0f + nu));
+    s.lam[p] = E * nu / ((1.0f + nu) * (1.0f - 2.0f * nu));
+}
+__global__ void mpm_bulk_kernel(const DevState s) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= s.n) return;
+    s.bulk[p] = s.lam[p] + 2.f / 3.f * s.mu[p];
+}
+__global__ void mpm_mass_kernel(const DevState s) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= s.n) return;
+    s.mass[p] = s.density[p] * s.vol[p];
+}
+__global__ void mpm_cov_from_F_kernel(const DevState s) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= s.n) return;
+    const M3 F = load_m3(s.F_trial, p);
+    const float* ic = s.init_cov + (size_t)p * 6;
+    M3 c0;
+    c0.m[0] = ic[0]; c0.m[1] = ic[1]; c0.m[2] = ic[2]; c0.m[3] = ic[1]; c0.m[4] = ic[3]; c0.m[5] = ic[4];
+    c0.m[6] = ic[2]; c0.m[7] = ic[4]; c0.m[8] = ic[5];
+    const M3 c = m3_mul_t(m3_mul(F, c0), F);
+    float* o = s.cov + (size_t)p * 6;
+    o[0] = c.m[0]; o[1] = c.m[1]; o[2] = c.m[2]; o[3] = c.m[4]; o[4] = c.m[5]; o[5] = c.m[8];
+}
+__global__ void mpm_R_from_F_kernel(const DevState s) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= s.n) return;
+    const M3 F = load_m3(s.F_trial, p);
+    M3 U, V; V3 sig;
+    svd3(F, U, sig, V);
+    // svd3 already returns proper rotations, so the det < 0 fix-ups of compute_R_from_F (:568-576) are no-ops
+    const M3 R = m3_mul_t(U, V);
+    store_m3(s.R, p, m3_t(R));
+}
+__global__ void mpm_additional_params_kernel(const DevState s, const float* __restrict__ boxes, int n_boxes) {
+    __shared__ float sb[128 * 10];
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    float px = 0, py = 0, pz = 0;
+    if (p < s.n) { px = s.x[3 * p]; py = s.x[3 * p + 1]; pz = s.x[3 * p + 2]; }
+    int hit = -1;
+    float hv[4] = {0, 0, 0, 0};
+    for (int b0 = 0; b0 < n_boxes; b0 += 128) {
+        const int nb = min(128, n_boxes - b0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < nb * 10; i += blockDim.x) sb[i] = boxes[(size_t)b0 * 10 + i];
+        __syncthreads();
+        for (int b = 0; b < nb; ++b) {
+            const float* B = sb + b * 10;
+            if (px > B[0] - B[3] && px < B[0] + B[3] && py > B[1] - B[4] && py < B[1] + B[4] &&
+                pz > B[2] - B[5] && pz < B[2] + B[5]) {
+                hit = b0 + b; hv[0] = B[6]; hv[1] = B[7]; hv[2] = B[8]; hv[3] = B[9];   // later boxes override
+            }
+        }
+    }
+    if (p < s.n && hit >= 0) {
+        s.E[p] = hv[0]; s.nu[p] = hv[1]; s.density[p] = hv[2]; s.material[p] = (int)hv[3];
+    }
+}
+__global__ void mpm_select_box_kernel(const DevState s, float3 point, float3 size, int* mask) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= s.n) return;
+    const float ox = s.x[3 * p] - point.x, oy = s.x[3 * p + 1] - point.y, oz = s.x[3 * p + 2] - point.z;
+    mask[p] = (fabsf(ox) < size.x && fabsf(oy) < size.y && fabsf(oz) < size.z) ? 1 : 0;
+}
+__global__ void mpm_select_cyl_kernel(const DevState s, float3 point, float3 normal, float half_height, float radius, int* mask) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= s.n) return;
+    const float ox = s.x[3 * p] - point.x, oy = s.x[3 * p + 1] - point.y, oz = s.x[3 * p + 2] - point.z;
+    const float on = ox * normal.x + oy * normal.y + oz * normal.z;
+    const float vd = fabsf(on);
+    const float hx = ox - on * normal.x, hy = oy - on * normal.y, hz = oz - on * normal.z;
+    const float hd = sqrtf(hx * hx + hy * hy + hz * hz);
+    mask[p] = (vd < half_height && hd < radius) ? 1 : 0;
+}
+
+}  // namespace
+
+// ============================================================================================ host
+struct Mpm {
+    int n = 0, n_grid = 0;
+    float grid_lim = 1.f;
+    void* fields[PIXIE_MPM_FIELD_COUNT] = {nullptr};
+    pixie_mpm_params params{};
+    std::vector<DevBC> bcs;
+    bool bcs_dirty = true;
+    float4* grid_mv = nullptr;
+    float4* grid_v = nullptr;
+    double* d_time = nullptr;
+    DevBC* d_bcs = nullptr;
+    // CUDA graph of kGraphSteps substeps, keyed by dt and the state snapshot it was captured with
+    cudaGraphExec_t graph = nullptr;
+    double graph_dt = 0;
+    bool graph_valid = false;
+    std::string error;
+};
+
+static constexpr int kGraphSteps = 25;
+
+static DevState make_state(Mpm* m) {
+    DevState s{};
+    auto f = [&](int id) { return reinterpret_cast<float*>(m->fields[id]); };
+    s.x = f(PIXIE_MPM_X); s.v = f(PIXIE_MPM_V); s.F = f(PIXIE_MPM_F); s.F_trial = f(PIXIE_MPM_F_TRIAL);
+    s.C = f(PIXIE_MPM_C); s.stress = f(PIXIE_MPM_STRESS); s.R = f(PIXIE_MPM_R); s.cov = f(PIXIE_MPM_COV);
+    s.init_cov = f(PIXIE_MPM_INIT_COV); s.vol = f(PIXIE_MPM_VOL); s.mass = f(PIXIE_MPM_MASS);
+    s.density = f(PIXIE_MPM_DENSITY); s.E = f(PIXIE_MPM_E); s.nu = f(PIXIE_MPM_NU); s.mu = f(PIXIE_MPM_MU);
+    s.lam = f(PIXIE_MPM_LAM); s.bulk = f(PIXIE_MPM_BULK); s.yield_stress = f(PIXIE_MPM_YIELD);
+    s.material = reinterpret_cast<int*>(m->fields[PIXIE_MPM_MATERIAL]);
+    s.selection = reinterpret_cast<int*>(m->fields[PIXIE_MPM_SELECTION]);
+    s.grid_mv = m->grid_mv; s.grid_v = m->grid_v; s.time = m->d_time; s.bcs = m->d_bcs; s.n_bc = (int)m->bcs.size();
+    s.n = m->n; s.n_grid = m->n_grid;
+    // dx, inv_dx exactly as mpm_solver_warp.py:61-66 (Python doubles rounded to fp32 members)
+    s.dx = (float)((double)m->grid_lim / (double)m->n_grid);
+    s.inv_dx = (float)((double)m->n_grid / (double)m->grid_lim);
+    const pixie_mpm_params& q = m->params;
+    s.gx = q.gravity[0]; s.gy = q.gravity[1]; s.gz = q.gravity[2];
+    s.rpic_damping = q.rpic_damping; s.grid_v_damping_scale = q.grid_v_damping_scale; s.alpha = q.alpha;
+    s.hardening = q.hardening; s.xi = q.xi; s.plastic_viscosity = q.plastic_viscosity; s.softening = q.softening;
+    s.update_cov_with_F = q.update_cov_with_F;
+    return s;
+}
+
+Mpm* mpm_create(int n_particles, int n_grid, float grid_lim, std::string& err) {
+    if (n_particles <= 0 || n_grid <= 0) { err = "n_particles and n_grid must be positive"; return nullptr; }
+    auto* m = new Mpm();
+    m->n = n_particles; m->n_grid = n_grid; m->grid_lim = grid_lim;
+    m->params.n_grid = n_grid; m->params.grid_lim = grid_lim;
+    m->params.grid_v_damping_scale = 1.1f;                 // mpm_solver_warp.py:92
+    {
+        // friction_angle 25 deg default (:83-86), evaluated like the reference (float math on 3.14159265)
+        const double sin_phi = sin(25.0 / 180.0 * 3.14159265);
+        m->params.alpha = (float)(sqrt(2.0 / 3.0) * 2.0 * sin_phi / (3.0 - sin_phi));
+    }
+    m->params.softening = 0.1f;
+    const size_t nodes = (size_t)n_grid * n_grid * n_grid;
+    if (cudaMalloc(&m->grid_mv, nodes * sizeof(float4)) != cudaSuccess ||
+        cudaMalloc(&m->grid_v, nodes * sizeof(float4)) != cudaSuccess ||
+        cudaMalloc(&m->d_time, sizeof(double)) != cudaSuccess ||
+        cudaMalloc(&m->d_bcs, kMaxBC * sizeof(DevBC)) != cudaSuccess) {
+        err = "cudaMalloc failed (no CUDA device?)";
+        delete m;
+        return nullptr;
+    }
+    cudaMemset(m->grid_mv, 0, nodes * sizeof(float4));
+    cudaMemset(m->grid_v, 0, nodes * sizeof(float4));
+    cudaMemset(m->d_time, 0, sizeof(double));
+    return m;
+}
+
+void mpm_destroy(Mpm* m) {
+    if (!m) return;
+    if (m->graph) cudaGraphExecDestroy(m->graph);
+    cudaFree(m->grid_mv); cudaFree(m->grid_v); cudaFree(m->d_time); cudaFree(m->d_bcs);
+    delete m;
+}
+
+int mpm_bind(Mpm* m, int field, void* ptr) {
+    if (field < 0 || field >= PIXIE_MPM_FIELD_COUNT) { m->error = "bad field id"; return 1; }
+    m->fields[field] = ptr;
+    m->graph_valid = false;
+    return 0;
+}
+int mpm_set_params(Mpm* m, const pixie_mpm_params& p) {
+    if (p.n_grid != m->n_grid) {
+        // set_parameters_dict re-allocates the grids when n_grid changes (mpm_solver_warp.py:318-343)
+        cudaFree(m->grid_mv); cudaFree(m->grid_v);
+        const size_t nodes = (size_t)p.n_grid * p.n_grid * p.n_grid;
+        if (cudaMalloc(&m->grid_mv, nodes * sizeof(float4)) != cudaSuccess ||
+            cudaMalloc(&m->grid_v, nodes * sizeof(float4)) != cudaSuccess) { m->error = "cudaMalloc failed"; return 1; }
+        cudaMemset(m->grid_mv, 0, nodes * sizeof(float4));
+        cudaMemset(m->grid_v, 0, nodes * sizeof(float4));
+        m->n_grid = p.n_grid;
+    }
+    m->grid_lim = p.grid_lim;
+    m->params = p;
+    m->graph_valid = false;
+    return 0;
+}
+int mpm_add_bc(Mpm* m, const pixie_mpm_bc& b) {
+    if ((int)m->bcs.size() >= kMaxBC) { m->error = "too many boundary conditions"; return 1; }
+    if (b.kind >= PIXIE_BC_IMPULSE && !b.mask_dev) { m->error = "particle BC needs a mask"; return 1; }
+    DevBC d{};
+    d.kind = b.kind;
+    for (int i = 0; i < 3; ++i) {
+        d.point[i] = b.point[i]; d.normal[i] = b.normal[i]; d.size[i] = b.size[i]; d.velocity[i] = b.velocity[i];
+        d.h1[i] = b.horizontal_axis_1[i]; d.h2[i] = b.horizontal_axis_2[i];
+    }
+    d.hhr[0] = b.half_height_and_radius[0]; d.hhr[1] = b.half_height_and_radius[1];
+    d.start_time = b.start_time; d.end_time = b.end_time; d.friction = b.friction;
+    d.surface_type = b.surface_type; d.reset = b.reset;
+    d.rotation_scale = b.rotation_scale; d.translation_scale = b.translation_scale;
+    d.mask = b.mask_dev;
+    m->bcs.push_back(d);
+    // append in place: the device table also holds the *moved* cuboid positions of earlier BCs
+    cudaMemcpy(m->d_bcs + (m->bcs.size() - 1), &d, sizeof(DevBC), cudaMemcpyHostToDevice);
+    m->graph_valid = false;
+    return 0;
+}
+int mpm_clear_bcs(Mpm* m) { m->bcs.clear(); m->graph_valid = false; return 0; }
+int mpm_set_time(Mpm* m, double t) { return cudaMemcpy(m->d_time, &t, sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess; }
+int mpm_get_time(Mpm* m, double* t) { return cudaMemcpy(t, m->d_time, sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess; }
+
+static int check_bound(Mpm* m) {
+    static const int need[] = {PIXIE_MPM_X, PIXIE_MPM_V, PIXIE_MPM_F, PIXIE_MPM_F_TRIAL, PIXIE_MPM_C, PIXIE_MPM_STRESS,
+                               PIXIE_MPM_VOL, PIXIE_MPM_MASS, PIXIE_MPM_MU, PIXIE_MPM_LAM, PIXIE_MPM_BULK,
+                               PIXIE_MPM_YIELD, PIXIE_MPM_MATERIAL, PIXIE_MPM_SELECTION};
+    for (int id : need)
+        if (!m->fields[id]) { m->error = "field " + std::to_string(id) + " is not bound"; return 1; }
+    if (m->params.update_cov_with_F && !m->fields[PIXIE_MPM_COV]) { m->error = "cov not bound"; return 1; }
+    return 0;
+}
+
+static void launch_substep(const DevState& s, float dt, double dt_d, cudaStream_t st) {
+    const int n = s.n;
+    const size_t nodes = (size_t)s.n_grid * s.n_grid * s.n_grid;
+    mpm_p2g_kernel<<<(n + 127) / 128, 128, 0, st>>>(s, dt);
+    mpm_grid_kernel<<<(unsigned)((nodes + 255) / 256), 256, 0, st>>>(s, dt);
+    mpm_g2p_kernel<<<(n + 127) / 128, 128, 0, st>>>(s, dt, dt_d);
+}
+
+int mpm_step(Mpm* m, int n_substeps, double dt_d, cudaStream_t st) {
+    if (check_bound(m)) return 1;
+    const float dt = (float)dt_d;
+    const DevState s = make_state(m);
+    int done = 0;
+    if (n_substeps >= kGraphSteps) {
+        if (!m->graph_valid || m->graph_dt != dt_d) {
+            if (m->graph) { cudaGraphExecDestroy(m->graph); m->graph = nullptr; }
+            cudaStream_t cs;
+            cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking);
+            cudaGraph_t g = nullptr;
+            bool ok = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+            if (ok) {
+                for (int i = 0; i < kGraphSteps; ++i) launch_substep(s, dt, dt_d, cs);
+                ok = cudaStreamEndCapture(cs, &g) == cudaSuccess && g;
+            }
+            if (ok) ok = cudaGraphInstantiate(&m->graph, g, 0) == cudaSuccess;
+            if (g) cudaGraphDestroy(g);
+            cudaStreamDestroy(cs);
+            if (!ok) { cudaGetLastError(); m->graph = nullptr; }
+            m->graph_valid = ok;
+            m->graph_dt = dt_d;
+        }
+        if (m->graph_valid) {
+            while (n_substeps - done >= kGraphSteps) {
+                if (cudaGraphLaunch(m->graph, st) != cudaSuccess) { m->error = "cudaGraphLaunch failed"; return 1; }
+                done += kGraphSteps;
+            }
+        }
+    }
+    for (; done < n_substeps; ++done) launch_substep(s, dt, dt_d, st);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { m->error = std::string("kernel launch failed: ") + cudaGetErrorString(e); return 1; }
+    return 0;
+}
+
+#define PIXIE_SIMPLE_LAUNCH(kernel)                                                         \
+    const DevState s = make_state(m);                                                       \
+    kernel<<<(m->n + 255) / 256, 256, 0, st>>>(s);                                          \
+    const cudaError_t e = cudaGetLastError();                                               \
+    if (e != cudaSuccess) { m->error = cudaGetErrorString(e); return 1; }                   \
+    return 0;
+
+int mpm_compute_mu_lam(Mpm* m, cudaStream_t st) { PIXIE_SIMPLE_LAUNCH(mpm_mu_lam_kernel) }
+int mpm_compute_bulk(Mpm* m, cudaStream_t st) { PIXIE_SIMPLE_LAUNCH(mpm_bulk_kernel) }
+int mpm_compute_mass(Mpm* m, cudaStream_t st) { PIXIE_SIMPLE_LAUNCH(mpm_mass_kernel) }
+int mpm_compute_cov_from_F(Mpm* m, cudaStream_t st) { PIXIE_SIMPLE_LAUNCH(mpm_cov_from_F_kernel) }
+int mpm_compute_R_from_F(Mpm* m, cudaStream_t st) { PIXIE_SIMPLE_LAUNCH(mpm_R_from_F_kernel) }
+
+int mpm_apply_additional_params(Mpm* m, const float* boxes_host, int n_boxes, cudaStream_t st) {
+    if (n_boxes <= 0) return 0;
+    float* d = nullptr;
+    if (cudaMalloc(&d, (size_t)n_boxes * 10 * 4) != cudaSuccess) { m->error = "cudaMalloc failed"; return 1; }
+    cudaMemcpyAsync(d, boxes_host, (size_t)n_boxes * 10 * 4, cudaMemcpyHostToDevice, st);
+    const DevState s = make_state(m);
+    mpm_additional_params_kernel<<<(m->n + 127) / 128, 128, 0, st>>>(s, d, n_boxes);
+    cudaStreamSynchronize(st);
+    cudaFree(d);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { m->error = cudaGetErrorString(e); return 1; }
+    return 0;
+}
+int mpm_select_box(Mpm* m, const float* point, const float* size, int* mask, cudaStream_t st) {
+    const DevState s = make_state(m);
+    mpm_select_box_kernel<<<(m->n + 255) / 256, 256, 0, st>>>(s, make_float3(point[0], point[1], point[2]),
+                                                              make_float3(size[0], size[1], size[2]), mask);
+    return cudaGetLastError() != cudaSuccess;
+}
+int mpm_select_cylinder(Mpm* m, const float* point, const float* normal, float hh, float radius, int* mask, cudaStream_t st) {
+    const DevState s = make_state(m);
+    mpm_select_cyl_kernel<<<(m->n + 255) / 256, 256, 0, st>>>(s, make_float3(point[0], point[1], point[2]),
+                                                              make_float3(normal[0], normal[1], normal[2]), hh, radius, mask);
+    return cudaGetLastError() != cudaSuccess;
+}
+int mpm_grid_ptrs(Mpm* m, float** mv4, float** v4) {
+    *mv4 = reinterpret_cast<float*>(m->grid_mv);
+    *v4 = reinterpret_cast<float*>(m->grid_v);
+    return 0;
+}
+const std::string& mpm_error(Mpm* m) { return m->error; }
+
+}  // namespace pixie

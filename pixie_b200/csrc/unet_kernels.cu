@@ -1,0 +1,262 @@
+// Memory-bound companions of the tcgen05 convolution on the U-Net path (sm_100a):
+//   * per-(sample, channel) moment reduction        (LayerNorm[D,H,W] / GroupNorm statistics)
+//   * normalise + affine + activation + fp16 cast   (the A operand of the next convolution)
+//   * nearest x2 upsample + fp16 cast               (diffusion_network.py:69, F.interpolate)
+//   * single-head attention over the bottleneck     (diffusion_network.py:213-242)
+// All activations are channels-last: x[nb][voxel][channel], fp32 in, fp16 out.
+#include "unet_kernels.cuh"
+
+#include <cuda_fp16.h>
+#include <cstdint>
+
+namespace pixie {
+
+namespace {
+
+__device__ __forceinline__ float act_apply(float v, int act) {
+    if (act == kActLeaky) return v > 0.f ? v : 0.02f * v;            // nn.LeakyReLU(0.02), training_discrete.py:80
+    if (act == kActSiLU) return v / (1.f + __expf(-v));              // nn.SiLU
+    return v;
+}
+
+// Packs 4 floats to fp16 (hi) and, when lo != nullptr, the rounding residual f - float(hi) to fp16.
+__device__ __forceinline__ void store_hi_lo(const float (&f)[4], __half* hi, __half* lo, size_t idx) {
+    __half2 r0 = __floats2half2_rn(f[0], f[1]), r1 = __floats2half2_rn(f[2], f[3]);
+    uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&r0); pk.y = *reinterpret_cast<uint32_t*>(&r1);
+    *reinterpret_cast<uint2*>(hi + idx) = pk;
+    if (lo) {
+        const float2 b0 = __half22float2(r0), b1 = __half22float2(r1);
+        __half2 l0 = __floats2half2_rn(f[0] - b0.x, f[1] - b0.y), l1 = __floats2half2_rn(f[2] - b1.x, f[3] - b1.y);
+        uint2 pl; pl.x = *reinterpret_cast<uint32_t*>(&l0); pl.y = *reinterpret_cast<uint32_t*>(&l1);
+        *reinterpret_cast<uint2*>(lo + idx) = pl;
+    }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------ moments
+// grid = (ceil(V / vox_per_block), NB), block = 256.  C % 4 == 0, C/4 <= 256.
+__global__ void __launch_bounds__(256)
+moments_kernel(const float* __restrict__ x, int V, int C, int vox_per_block, double* __restrict__ stats) {
+    const int cols4 = C >> 2;
+    const int rows_par = 256 / cols4;
+    const int col = threadIdx.x % cols4;
+    const int row = threadIdx.x / cols4;
+    const int nb = blockIdx.y;
+    const int v0 = blockIdx.x * vox_per_block;
+    const int v1 = min(V, v0 + vox_per_block);
+    float s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
+    if (row < rows_par) {
+        const float4* xp = reinterpret_cast<const float4*>(x + ((size_t)nb * V) * C) + col;
+        for (int v = v0 + row; v < v1; v += rows_par) {
+            const float4 a = __ldg(xp + (size_t)v * cols4);
+            s[0] += a.x; s[1] += a.y; s[2] += a.z; s[3] += a.w;
+            q[0] += a.x * a.x; q[1] += a.y * a.y; q[2] += a.z * a.z; q[3] += a.w * a.w;
+        }
+    }
+    __shared__ float sh[256 * 8];
+    float* mine = sh + threadIdx.x * 8;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { mine[j] = s[j]; mine[4 + j] = q[j]; }
+    __syncthreads();
+    if (threadIdx.x < cols4) {
+        double ds[4] = {0, 0, 0, 0}, dq[4] = {0, 0, 0, 0};
+        for (int r = 0; r < rows_par; ++r) {
+            const float* o = sh + (r * cols4 + threadIdx.x) * 8;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { ds[j] += o[j]; dq[j] += o[4 + j]; }
+        }
+        double* st = stats + ((size_t)nb * C + threadIdx.x * 4) * 2;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            atomicAdd(st + 2 * j, ds[j]);
+            atomicAdd(st + 2 * j + 1, dq[j]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------ normalise
+// y = act((x - mean) * rstd * gamma + beta) -> fp16; optional raw fp16 copy of x.
+// mode LN : statistics per (nb, c) over V; gamma/beta indexed by voxel   (nn.LayerNorm([sp,sp,sp]))
+// mode GN : statistics per (nb, group) over V x cg channels; gamma/beta indexed by channel
+// mode NONE: cast only (raw copy).
+__global__ void __launch_bounds__(256)
+norm_act_kernel(NormArgs a) {
+    const int cols4 = a.C >> 2;
+    const int rows_par = 256 / cols4;
+    const int col = threadIdx.x % cols4;
+    const int row = threadIdx.x / cols4;
+    if (row >= rows_par) return;
+    const int nb = blockIdx.y;
+    const int c = col * 4;
+    float mean[4] = {0, 0, 0, 0}, rstd[4] = {1, 1, 1, 1}, g[4] = {1, 1, 1, 1}, b[4] = {0, 0, 0, 0};
+    if (a.mode != kNormNone) {
+        const int cg = (a.mode == kNormGN) ? a.C / a.groups : 1;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int grp0 = ((c + j) / cg) * cg;
+            double s = 0, q = 0;
+            for (int k = 0; k < cg; ++k) {
+                s += a.stats[((size_t)nb * a.C + grp0 + k) * 2];
+                q += a.stats[((size_t)nb * a.C + grp0 + k) * 2 + 1];
+            }
+            const double n = (double)a.V * cg;
+            const double m = s / n;
+            double var = q / n - m * m;
+            if (var < 0) var = 0;
+            mean[j] = (float)m;
+            rstd[j] = (float)(1.0 / sqrt(var + (double)a.eps));
+            if (a.mode == kNormGN) { g[j] = a.gamma[c + j]; b[j] = a.beta[c + j]; }
+        }
+    }
+    const int v0 = blockIdx.x * a.vox_per_block;
+    const int v1 = min(a.V, v0 + a.vox_per_block);
+    const float4* xp = reinterpret_cast<const float4*>(a.x + ((size_t)nb * a.V) * a.C) + col;
+    for (int v = v0 + row; v < v1; v += rows_par) {
+        const float4 xv = __ldg(xp + (size_t)v * cols4);
+        float f[4] = {xv.x, xv.y, xv.z, xv.w};
+        if (a.raw_dst) store_hi_lo(f, a.raw_dst, a.raw_lo, ((size_t)nb * a.V + v) * a.raw_ld + a.raw_c0 + c);
+        if (a.dst) {
+            float gv = 1.f, bv = 0.f;
+            if (a.mode == kNormLN) { gv = __ldg(a.gamma + v); bv = __ldg(a.beta + v); }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float y = f[j];
+                if (a.mode == kNormLN) y = (y - mean[j]) * rstd[j] * gv + bv;
+                else if (a.mode == kNormGN) y = (y - mean[j]) * rstd[j] * g[j] + b[j];
+                f[j] = act_apply(y, a.act);
+            }
+            store_hi_lo(f, a.dst, a.dst_lo, ((size_t)nb * a.V + v) * a.dst_ld + a.dst_c0 + c);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------ upsample x2
+// in: fp32 [NB][sp^3][C]; out: fp16 [NB][(2sp)^3][C], nearest neighbour.
+__global__ void __launch_bounds__(256)
+upsample2_kernel(const float* __restrict__ x, __half* __restrict__ y, __half* __restrict__ ylo, int sp, int C, long long total4) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total4) return;
+    const int cols4 = C >> 2;
+    const int col = (int)(i % cols4);
+    long long v = i / cols4;
+    const int S = 2 * sp;
+    const int w = (int)(v % S); v /= S;
+    const int h = (int)(v % S); v /= S;
+    const int d = (int)(v % S); v /= S;
+    const long long nb = v;
+    const long long src = ((nb * sp + (d >> 1)) * sp + (h >> 1)) * sp + (w >> 1);
+    const float4 a = __ldg(reinterpret_cast<const float4*>(x + src * C) + col);
+    const float f[4] = {a.x, a.y, a.z, a.w};
+    store_hi_lo(f, y, ylo, (size_t)i * 4);
+}
+
+// ------------------------------------------------------------------------------------ attention
+// qkv: fp32 [NB][T][3C] (q | k | v along channels, Conv1d output order, diffusion_network.py:233)
+// out: fp16 [NB][T][C] = softmax_s((q_t . k_s) / sqrt(C)) v_s.   One block per (query token, nb).
+__global__ void __launch_bounds__(256)
+attention_kernel(const float* __restrict__ qkv, __half* __restrict__ out, __half* __restrict__ out_lo, int T, int C) {
+    extern __shared__ float sm[];
+    float* qs = sm;            // C
+    float* sc = sm + C;        // T
+    __shared__ float red[32];
+    const int t = blockIdx.x, nb = blockIdx.y;
+    const float* base = qkv + (size_t)nb * T * 3 * C;
+    const float scale = rsqrtf(sqrtf((float)C));     // applied to q and to k (diffusion_network.py:235-238)
+    for (int c = threadIdx.x; c < C; c += blockDim.x) qs[c] = base[(size_t)t * 3 * C + c] * scale;
+    __syncthreads();
+    float lmax = -INFINITY;
+    for (int s = threadIdx.x; s < T; s += blockDim.x) {
+        const float4* kp = reinterpret_cast<const float4*>(base + (size_t)s * 3 * C + C);
+        float acc = 0.f;
+        for (int c4 = 0; c4 < C / 4; ++c4) {
+            const float4 kv = __ldg(kp + c4);
+            acc += qs[4 * c4] * (kv.x * scale) + qs[4 * c4 + 1] * (kv.y * scale) +
+                   qs[4 * c4 + 2] * (kv.z * scale) + qs[4 * c4 + 3] * (kv.w * scale);
+        }
+        sc[s] = acc;
+        lmax = fmaxf(lmax, acc);
+    }
+    // block max
+    for (int o = 16; o; o >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffff, lmax, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = lmax;
+    __syncthreads();
+    float bmax = red[0];
+    for (int i = 1; i < (int)(blockDim.x >> 5); ++i) bmax = fmaxf(bmax, red[i]);
+    __syncthreads();
+    float lsum = 0.f;
+    for (int s = threadIdx.x; s < T; s += blockDim.x) {
+        const float e = __expf(sc[s] - bmax);
+        sc[s] = e;
+        lsum += e;
+    }
+    for (int o = 16; o; o >>= 1) lsum += __shfl_xor_sync(0xffffffff, lsum, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = lsum;
+    __syncthreads();
+    float bsum = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) bsum += red[i];
+    const float inv = 1.f / bsum;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float acc = 0.f;
+        for (int s = 0; s < T; ++s) acc += sc[s] * __ldg(base + (size_t)s * 3 * C + 2 * C + c);
+        const float val = acc * inv;
+        const __half hv = __float2half_rn(val);
+        out[((size_t)nb * T + t) * C + c] = hv;
+        if (out_lo) out_lo[((size_t)nb * T + t) * C + c] = __float2half_rn(val - __half2float(hv));
+    }
+}
+
+// NCDHW fp32 -> NDHWC fp16 (channel-padded), for callers that hand over the reference's input layout
+// (my_data.py:221 permute(3,0,1,2)) instead of the on-disk one.
+__global__ void __launch_bounds__(256)
+ncdhw_to_ndhwc_f16_kernel(const float* __restrict__ x, __half* __restrict__ y, int C, int Cpad, long long V) {
+    // one thread per (voxel, channel) of the padded output; reads are strided, used off the hot path only
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int nb = blockIdx.y;
+    if (i >= V * Cpad) return;
+    const int c = (int)(i % Cpad);
+    const long long v = i / Cpad;
+    const float val = c < C ? x[((size_t)nb * C + c) * V + v] : 0.f;
+    y[(size_t)nb * V * Cpad + i] = __float2half_rn(val);
+}
+
+// ------------------------------------------------------------------------------------ launchers
+static inline int vox_per_block_for(int V) { return V >= 4096 ? 256 : 64; }
+
+int launch_moments(const float* x, int NB, int V, int C, double* stats, cudaStream_t st) {
+    if (C % 4 || C / 4 > 256) return 1;
+    const int vpb = vox_per_block_for(V);
+    dim3 grid((V + vpb - 1) / vpb, NB);
+    moments_kernel<<<grid, 256, 0, st>>>(x, V, C, vpb, stats);
+    return (int)cudaGetLastError();
+}
+
+int launch_norm_act(NormArgs a, int NB, cudaStream_t st) {
+    if (a.C % 4 || a.C / 4 > 256) return 1;
+    a.vox_per_block = vox_per_block_for(a.V);
+    dim3 grid((a.V + a.vox_per_block - 1) / a.vox_per_block, NB);
+    norm_act_kernel<<<grid, 256, 0, st>>>(a);
+    return (int)cudaGetLastError();
+}
+
+int launch_upsample2(const float* x, __half* y, __half* ylo, int NB, int sp, int C, cudaStream_t st) {
+    const long long total4 = (long long)NB * 8 * sp * sp * sp * (C / 4);
+    upsample2_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, st>>>(x, y, ylo, sp, C, total4);
+    return (int)cudaGetLastError();
+}
+
+int launch_attention(const float* qkv, __half* out, __half* out_lo, int NB, int T, int C, cudaStream_t st) {
+    const size_t smem = (size_t)(C + T) * sizeof(float);
+    if (smem > 48 * 1024) return 1;
+    dim3 grid(T, NB);
+    attention_kernel<<<grid, 256, smem, st>>>(qkv, out, out_lo, T, C);
+    return (int)cudaGetLastError();
+}
+
+int launch_ncdhw_to_ndhwc_f16(const float* x, __half* y, int NB, int C, int Cpad, long long V, cudaStream_t st) {
+    dim3 grid((unsigned)((V * Cpad + 255) / 256), NB);
+    ncdhw_to_ndhwc_f16_kernel<<<grid, 256, 0, st>>>(x, y, C, Cpad, V);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace pixie
