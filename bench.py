@@ -1,0 +1,379 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the pixie_b200 hot path (contract: see the build prompt / DESIGN.md).
+
+    python bench.py --gpus 1 --steps K --warmup W              # our arm (CUDA, through the C ABI)
+    python bench.py --impl reference --steps K --warmup W      # reference arm: the CPU path on host cores
+    torchrun --nproc-per-node N ... bench.py --gpus N ...      # one rank per GPU, scenes sharded, weak scaling
+
+One "step" = one scene of BASELINE.json configs[1] + configs[2]:
+    material field   : SegmentationUNet + RegressionUNet forward on a 64^3 x 512 fp16 voxel grid
+    physics rollout  : 1000 MPM substeps of 100k particles on a 64^3 grid
+The two halves are timed in two separate regions of exactly K steps each (barrier + synchronize on both
+sides, CUDA events on the launching stream, max over ranks); `value` is the U-Net voxels/s, the MPM
+particle-steps/s is reported under "mpm"; `ms_per_step` is the sum of both per-step times.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+UNET_CFG = dict(cond_dim=32, model_channels=64, num_res_blocks=3, channel_mult=(1, 1, 2, 4), attention_resolutions=())
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tensor_burst=d["bf16_tflops"], tensor=d["bf16_tflops_sustained"], src="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tensor_burst=1590.0, tensor=1400.0, src="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (recipe of B200_PROFILING.md)."""
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        load = [s for s in sm if s > 0.6 * max(sm)] if sm else []
+        return {"sm_mhz": float(np.median(load)) if load else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ workloads
+def make_state_dicts(C, G):
+    """Seeded parameters for the two networks (reference key names / shapes)."""
+    from pixie_b200.synthetic import seeded_state_dict
+    from pixie_b200.unet import _expected_keys
+    mk = lambda out, seed: seeded_state_dict(_expected_keys(C, UNET_CFG["cond_dim"], UNET_CFG["model_channels"],
+                                                            UNET_CFG["num_res_blocks"], UNET_CFG["channel_mult"], G, out), seed)
+    return mk(8, 0), mk(3, 1)
+
+
+def make_unet_oracle(C, G):
+    """CPU baseline / reference arm only: the restated reference modules with the same parameters."""
+    from oracle import unet_ref as O
+    cfg = dict(UNET_CFG)
+    seg = O.SegmentationUNet(feature_channels=C, grid_size=G, num_classes=8, **cfg).eval()
+    reg = O.RegressionUNet(feature_channels=C, grid_size=G, out_channels=3, **cfg).eval()
+    sd_seg, sd_reg = make_state_dicts(C, G)
+    seg.load_state_dict(sd_seg); reg.load_state_dict(sd_reg)
+    return seg, reg
+
+
+def make_features(G, C, seed):
+    from pixie_b200.synthetic import synthetic_features_ndhwc
+    return synthetic_features_ndhwc(1, C, G, seed=seed)                            # on-disk layout, fp16 NDHWC
+
+
+def make_mpm_scene(n, ng, seed):
+    from pixie_b200.synthetic import synthetic_scene
+    return synthetic_scene(n, ng, seed=seed, materials=(0,))
+
+
+def setup_solver(sc, ng, dev):
+    from pixie_b200.mpm_solver_warp import MPM_Simulator_WARP
+    s = MPM_Simulator_WARP(10, device=dev)
+    t = lambda a: torch.from_numpy(a).to(dev)
+    s.load_initial_data_from_torch(t(sc["x"]), t(sc["vol"]), None, n_grid=ng, grid_lim=2.0, device=dev)
+    s.set_parameters_dict({"material": "jelly", "g": [0.0, 0.0, -9.8], "density": 1000.0, "E": 1e5, "nu": 0.3,
+                           "grid_v_damping_scale": 0.9999, "rpic_damping": 0.0}, device=dev)
+    s.mpm_model.E = t(sc["E"]); s.mpm_model.nu = t(sc["nu"])
+    s.reset_densities_and_update_masses(t(sc["density"]))
+    s.import_particle_v_from_torch(t(sc["v"]))
+    s.finalize_mu_lam()
+    s.add_bounding_box()
+    s.set_velocity_on_cuboid(point=[1.0, 1.0, 0.62], size=[0.5, 0.5, 0.04], velocity=[0, 0, 0])   # "stationary" cluster pin
+    s.add_impulse_on_particles(force=[0.05, 0.0, -0.02], dt=1e-4, point=[1.0, 1.0, 1.2], size=[0.2, 0.2, 0.1], num_dt=20)
+    return s
+
+
+def setup_oracle_mpm(sc, ng, parallel=1):
+    from oracle import mpm_ref as R
+    n = sc["x"].shape[0]
+    o = R.MpmRef(n, ng, 2.0, "f32")
+    for k, f in (("x", "X"), ("v", "V"), ("vol", "VOL"), ("density", "DENSITY"), ("E", "E"), ("nu", "NU"), ("material", "MATERIAL")):
+        o.set(f, sc[k])
+    o.compute_mass(); o.compute_mu_lam()
+    o.set_params(g=(0, 0, -9.8), grid_v_damping_scale=0.9999, parallel_p2g=parallel)
+    o.add_bc(R.BC_BBOX)
+    o.add_bc(R.BC_CUBOID, point=[1.0, 1.0, 0.62], size=[0.5, 0.5, 0.04])
+    mask = (np.abs(sc["x"] - np.float32([1.0, 1.0, 1.2])) < np.float32([0.2, 0.2, 0.1])).all(1).astype(np.int32)
+    o.add_bc(R.BC_IMPULSE, velocity=[0.05, 0.0, -0.02], start_time=0.0, end_time=20e-4, mask=mask)
+    return o
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def run_reference(args):
+    """The reference's own CPU implementation of the path on the host cores: the restated PyTorch modules
+    (oracle/unet_ref.py, bit-identical to the reference's — tests/test_oracle_unet.py) and the C
+    restatement of its Warp kernels (oracle/mpm_ref.c; warp-lang is not installable here)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    G, C, n, ng = args.grid, args.channels, args.particles, args.mpm_grid
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    seg, reg = make_unet_oracle(C, G)
+    x = make_features(G, C, 1).float().permute(0, 4, 1, 2, 3).contiguous()       # fp32 NCDHW, my_data.py:221
+    sc = make_mpm_scene(n, ng, 0)
+    o = setup_oracle_mpm(sc, ng)
+    sample_sub = args.ref_substeps
+    t_un, t_mp = [], []
+    for it in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            seg(x); reg(x)
+        t1 = time.perf_counter()
+        o.step(sample_sub, 1e-4)
+        t2 = time.perf_counter()
+        if it >= args.warmup:
+            t_un.append(t1 - t0); t_mp.append(t2 - t1)
+    vps = G ** 3 * len(t_un) / sum(t_un)
+    pps = n * sample_sub * len(t_mp) / sum(t_mp)
+    sample = f"U-Net: full seg+reg forward at {G}^3x{C} per step; MPM: {sample_sub} of {args.substeps} substeps of the {n}-particle scene per step"
+    line = {
+        "impl": "reference", "metric": "unet_voxels_per_s", "value": vps, "unit": "voxels/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * (sum(t_un) + sum(t_mp) * args.substeps / sample_sub) / len(t_un),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, "f32 (CPU)"),
+        "mpm": {"metric": "mpm_particle_steps_per_s", "value": pps, "unit": "particle-steps/s"},
+        "cpu_baseline": {"value": vps, "unit": "voxels/s", "cores": cores, "kind": "port", "sample": sample,
+                         "mpm_value": pps, "mpm_unit": "particle-steps/s", "mpm_threads": o.num_threads()},
+        "e2e": {"value": vps, "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, precision):
+    return {"workload": f"configs[1]+configs[2]: U-Net seg+reg forward on one {args.grid}^3x{args.channels} fp16 voxel grid, then "
+                        f"{args.substeps} MPM substeps of {args.particles} particles on a {args.mpm_grid}^3 grid; 1 scene per GPU per step",
+            "unet_precision": precision, "parallelism": f"scene-dp{args.gpus}",
+            "l2": "U-Net input grid (268 MB) and activations exceed the 126 MB L2; the MPM working set (36 MB/substep) is "
+                  "L2-resident by construction, a 256 MB buffer is written between timed steps"}
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch.distributed as dist
+    from pixie_b200 import _lib
+    from pixie_b200.inference import MaterialFieldPredictor
+
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    _lib.load()
+    torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+    G, C, n, ng, SUB = args.grid, args.channels, args.particles, args.mpm_grid, args.substeps
+    pk = peaks()
+
+    # ---- build: identical seeded weights on every rank (weights replicated, scenes sharded)
+    sd_seg, sd_reg = make_state_dicts(C, G)
+    pred = MaterialFieldPredictor(feature_channels=C, grid_size=G, device=dev, max_batch=1, precision=args.precision, **UNET_CFG)
+    pred.load_state_dicts(sd_seg, sd_reg)
+    feat_host = make_features(G, C, 1 + rank).pin_memory()
+    feat_dev = feat_host.to(dev)
+    sc = make_mpm_scene(n, ng, rank)
+    flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)        # 256 MB > L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup, prep=None):
+        """K steps of fn(), each preceded by an (untimed, event-excluded) L2 flush + prep; returns the
+        max-over-ranks sum of per-step device times in ms."""
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for _ in range(warmup):
+            if prep: prep()
+            fn()
+        barrier()
+        for i in range(steps):
+            if prep: prep()
+            flush.fill_(1.0)
+            ev[i][0].record(); fn(); ev[i][1].record()
+        barrier()
+        ms = sum(a.elapsed_time(b) for a, b in ev)
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+
+    # ---- region 1: material field (both networks), inputs resident in HBM
+    out_holder = {}
+    def unet_step():
+        out_holder["seg"], out_holder["cont"] = pred.predict(feat_dev)
+    ms_unet = timed(unet_step, args.steps, args.warmup)
+    pred.seg_network.check(); pred.cont_network.check()
+
+    # ---- region 2: MPM rollout, state resident; every step restarts from the same initial scene
+    solver = setup_solver(sc, ng, dev)
+    x0, v0 = solver.export_particle_x_to_torch().clone(), solver.export_particle_v_to_torch().clone()
+    def mpm_prep():
+        solver.export_particle_x_to_torch().copy_(x0); solver.export_particle_v_to_torch().copy_(v0)
+        solver._t["C"].zero_(); ft = solver._t["F_TRIAL"]; ft.zero_(); ft[:, 0, 0] = 1; ft[:, 1, 1] = 1; ft[:, 2, 2] = 1
+        solver.time = 0.0
+    def mpm_step():
+        solver.p2g2p_n(SUB, 1e-4)
+    ms_mpm = timed(mpm_step, args.steps, args.warmup, prep=mpm_prep)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- e2e: host buffers in, host results out, through the public API (per step: H2D grid, both nets,
+    #      pack, D2H field; H2D particles, rollout, D2H positions)
+    packed_host = torch.empty((1, 11, G, G, G), dtype=torch.float32).pin_memory()
+    host_scene = {k: torch.from_numpy(v).pin_memory() for k, v in sc.items() if k != "material"}
+    x_out_host = torch.empty((n, 3), dtype=torch.float32).pin_memory()
+    def e2e_unet():
+        pred.predict_packed_host(feat_host, packed_host)
+    def e2e_mpm():
+        solver.export_particle_x_to_torch().copy_(host_scene["x"], non_blocking=True)
+        solver.export_particle_v_to_torch().copy_(host_scene["v"], non_blocking=True)
+        solver._t["E"].copy_(host_scene["E"], non_blocking=True); solver._t["NU"].copy_(host_scene["nu"], non_blocking=True)
+        solver._t["DENSITY"].copy_(host_scene["density"], non_blocking=True); solver._t["VOL"].copy_(host_scene["vol"], non_blocking=True)
+        solver.reset_densities_and_update_masses(solver._t["DENSITY"]); solver.finalize_mu_lam()
+        solver.p2g2p_n(SUB, 1e-4)
+        x_out_host.copy_(solver.export_particle_x_to_torch(), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    ms_e2e_unet = timed(e2e_unet, args.steps, args.warmup)
+    ms_e2e_mpm = timed(e2e_mpm, args.steps, args.warmup, prep=mpm_prep)
+    h2d = feat_host.numel() * 2 + sum(t.numel() * 4 for t in host_scene.values())
+    d2h = packed_host.numel() * 4 + x_out_host.numel() * 4
+
+    # ---- live per-kernel numbers (rank 0): conv kernel share and achieved TFLOP/s; MPM substep bytes
+    roof, roof_mpm, breakdown, n_launch = None, None, None, None
+    if rank == 0:
+        prof = pred.seg_network.profile(feat_dev) + pred.cont_network.profile(feat_dev)
+        by = {}
+        for kind, ms, fl in prof:
+            a = by.setdefault(kind, [0, 0.0, 0.0]); a[0] += 1; a[1] += ms; a[2] += fl
+        conv_ms, conv_fl = by["conv"][1], by["conv"][2]
+        ach = conv_fl / (conv_ms * 1e-3) * 1e-12
+        roof = {"kernel": "conv3d_igemm_kernel (tcgen05 implicit GEMM), all convolutions of seg+reg", "bound": "tensor",
+                "achieved": ach, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": ach / pk["tensor"], "peak_burst": pk["tensor_burst"],
+                "peak_source": pk["src"] + ", sustained bf16", "traffic": None,
+                "note": "achieved = algorithmic FLOPs (2*MACs of the reference graph) / sum of conv launch times from CUDA events; "
+                        + ("fp16x3 executes 3 tensor-core passes per algorithmic FLOP" if args.precision == "fp16x3" else "1 tensor-core pass")}
+        breakdown = {k: {"launches": v[0], "ms": round(v[1], 4)} for k, v in by.items()}
+        per_sub_bytes = 212.0 * n + 56.0 * ng ** 3
+        sub_s = ms_mpm * 1e-3 / (args.steps * SUB)
+        roof_mpm = {"kernel": "mpm substep (p2g + grid + g2p launches)", "bound": "hbm", "achieved": per_sub_bytes / sub_s * 1e-9,
+                    "peak": pk["hbm"], "unit": "GB/s", "frac": per_sub_bytes / sub_s * 1e-9 / pk["hbm"], "peak_source": pk["src"],
+                    "traffic": None, "algorithmic_bytes_per_substep": per_sub_bytes, "us_per_substep": sub_s * 1e6}
+        n_launch = args.steps * (pred.seg_network.launch_count() + pred.cont_network.launch_count() + 3 * SUB)
+
+    # ---- parity of the benchmarked mode and CPU baseline (rank 0, N=1 only: bounded sample)
+    cpu, parity = None, None
+    if rank == 0 and world == 1 and not args.skip_cpu:
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        seg_o, reg_o = make_unet_oracle(C, G)
+        x32 = feat_host.float().permute(0, 4, 1, 2, 3).contiguous()
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            ys, yr = seg_o(x32), reg_o(x32)
+        t_cpu_unet = time.perf_counter() - t0
+        parity = {"unet_max_abs_err_cont": float((out_holder["cont"].cpu() - yr).abs().max()),
+                  "unet_max_abs_err_seg_logits": float((out_holder["seg"].cpu() - ys).abs().max()),
+                  "tolerance": 1e-3 if args.precision == "fp16x3" else 2e-2}
+        o = setup_oracle_mpm(sc, ng)
+        t0 = time.perf_counter(); o.step(args.ref_substeps, 1e-4); t_cpu_mpm = time.perf_counter() - t0
+        cpu = {"value": G ** 3 / t_cpu_unet, "unit": "voxels/s", "cores": cores, "kind": "port",
+               "sample": f"one seg+reg forward at {G}^3x{C} (oracle/unet_ref.py, fp32 torch CPU, {cores} threads); "
+                         f"MPM: {args.ref_substeps} substeps of the {n}-particle scene (oracle/mpm_ref.c fp32, OpenMP {o.num_threads()} threads)",
+               "mpm_value": n * args.ref_substeps / t_cpu_mpm, "mpm_unit": "particle-steps/s"}
+
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    K = args.steps
+    vps = world * G ** 3 * K / (ms_unet * 1e-3)
+    pps = world * n * SUB * K / (ms_mpm * 1e-3)
+    line = {
+        "metric": "unet_voxels_per_s", "value": vps, "unit": "voxels/s", "n_gpus": world, "steps": K, "warmup": args.warmup,
+        "ms_per_step": (ms_unet + ms_mpm) / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": ("fp16x3" if args.precision == "fp16x3" else "fp16") + " (U-Net, fp32 accumulate) + f32 (MPM)", "data": "synthetic",
+        "config": workload_config(args, args.precision),
+        "unet_ms_per_scene": ms_unet / K, "mpm_ms_per_rollout": ms_mpm / K,
+        "mpm": {"metric": "mpm_particle_steps_per_s", "value": pps, "unit": "particle-steps/s", "us_per_substep": ms_mpm / K / SUB * 1e3},
+        "roofline": roof, "roofline_mpm": roof_mpm, "unet_kernel_breakdown_ms": breakdown,
+        "cpu_baseline": cpu, "parity": parity,
+        "e2e": {"value": world * G ** 3 * K / (ms_e2e_unet * 1e-3), "unit": "voxels/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "mpm_value": world * n * SUB * K / (ms_e2e_mpm * 1e-3), "mpm_unit": "particle-steps/s",
+                "ms_per_step": (ms_e2e_unet + ms_e2e_mpm) / K},
+        "gpu_launches": n_launch, "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="fp16x3", choices=["fp16x3", "fp16"],
+                    help="fp16x3 (default) meets the 1e-3 material-field tolerance; fp16 is the single-pass mode")
+    ap.add_argument("--grid", type=int, default=64)
+    ap.add_argument("--channels", type=int, default=512)
+    ap.add_argument("--particles", type=int, default=100_000)
+    ap.add_argument("--mpm-grid", type=int, default=64)
+    ap.add_argument("--substeps", type=int, default=1000)
+    ap.add_argument("--ref-substeps", type=int, default=20, help="MPM substeps per step in the CPU sample")
+    ap.add_argument("--skip-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -69,6 +69,16 @@ int pixie_unet_forward_ncdhw(pixie_unet_t h, const float* feat_ncdhw_f32_dev, in
  * host->device and device->host copies are issued on `stream` inside the call; returns after sync. */
 int pixie_unet_forward_host(pixie_unet_t h, const void* feat_ndhwc_f16_host, int batch,
                             float* out_ncdhw_f32_host, void* stream);
+/* Per-launch device times of one forward (CUDA events on `stream`, after one warm-up forward):
+ * fills ms[i], kinds[i] (PIXIE_OP_*), flops[i] (algorithmic FLOPs, convolutions only) for each of the
+ * n launches and returns n (<0 on error). Used by bench.py for the live roofline numbers. */
+enum pixie_op_kind { PIXIE_OP_CONV = 0, PIXIE_OP_MOMENTS = 1, PIXIE_OP_NORM = 2, PIXIE_OP_UPSAMPLE = 3, PIXIE_OP_ATTENTION = 4 };
+int pixie_unet_profile(pixie_unet_t h, const void* feat_ndhwc_f16_dev, int batch, float* out_ncdhw_f32_dev,
+                       void* stream, float* ms, int* kinds, double* flops, int cap);
+/* save_predictions packing (inference_combined.py:173-199, argmax :125): (3 + n_classes, D, H, W) fp32 =
+ * continuous channels followed by the one-hot of argmax(seg_logits). All pointers device, planar NCDHW. */
+int pixie_pack_predictions(const float* seg_logits_dev, const float* cont_dev, float* out_dev, int batch,
+                           int64_t voxels, int n_classes, void* stream);
 /* Number of kernel launches one forward() issues (for gpu_launches accounting) and algorithmic
  * FLOPs of one forward at batch 1 (2 * MACs of every Conv3d/Conv1d of the reference graph). */
 int pixie_unet_launch_count(pixie_unet_t h);

@@ -49,7 +49,8 @@ enum { BC_SURFACE = 0, BC_CUBOID = 1, BC_BBOX = 2, BC_IMPULSE = 3, BC_VTRANS = 4
 typedef struct {
     int kind;
     real point[3], normal[3], size[3], velocity[3];
-    real start_time, end_time, friction;
+    float start_time, end_time;   /* compared against float(time) in BOTH builds, like the Warp kernels */
+    real friction;
     int surface_type, reset;
     real h1[3], h2[3], hhr[2], rotation_scale, translation_scale;
     int* mask;
@@ -418,7 +419,7 @@ static void g2p_particle(sim_t* s, int p, real dt) {
 }
 
 /* grid_normalization_and_gravity :398-409, add_damping_via_grid :583-588, BC collide closures */
-static void grid_node(sim_t* s, size_t idx, real time, real dt) {
+static void grid_node(sim_t* s, size_t idx, float time, real dt) {
     const int n = s->n_grid;
     const int gz = (int)(idx % n), gy = (int)((idx / n) % n), gx = (int)(idx / ((size_t)n * n));
     real* vo = s->grid_v_out + 3 * idx;
@@ -454,7 +455,7 @@ static void grid_node(sim_t* s, size_t idx, real time, real dt) {
                 if (RABS(off[0]) < bc->size[0] && RABS(off[1]) < bc->size[1] && RABS(off[2]) < bc->size[2])
                     for (int a = 0; a < 3; ++a) vo[a] = bc->velocity[a];
             } else if (bc->reset == 1) {
-                if (time < bc->end_time + (real)15.0 * dt) { vo[0] = vo[1] = vo[2] = 0; }
+                if (time < bc->end_time + 15.0f * (float)dt) { vo[0] = vo[1] = vo[2] = 0; }
             }
         } else if (bc->kind == BC_BBOX) {                        /* :917-974 */
             if (!active) continue;
@@ -470,7 +471,7 @@ static void grid_node(sim_t* s, size_t idx, real time, real dt) {
 }
 
 /* pre-p2g particle operations: impulses, then velocity modifiers (mpm_solver_warp.py:528-547) */
-static void particle_bcs(sim_t* s, int p, real time, real dt) {
+static void particle_bcs(sim_t* s, int p, float time, real dt) {
     real* v = s->f[F_V] + 3 * (size_t)p;
     const real* x = s->f[F_X] + 3 * (size_t)p;
     for (int k = 0; k < s->n_bc; ++k) {
@@ -568,7 +569,7 @@ void mpmref_add_bc(sim_t* s, int kind, const double* vals, int surface_type, int
         b->point[a] = (real)vals[a]; b->normal[a] = (real)vals[3 + a]; b->size[a] = (real)vals[6 + a];
         b->velocity[a] = (real)vals[9 + a]; b->h1[a] = (real)vals[15 + a]; b->h2[a] = (real)vals[18 + a];
     }
-    b->start_time = (real)vals[12]; b->end_time = (real)vals[13]; b->friction = (real)vals[14];
+    b->start_time = (float)vals[12]; b->end_time = (float)vals[13]; b->friction = (real)vals[14];
     b->hhr[0] = (real)vals[21]; b->hhr[1] = (real)vals[22]; b->rotation_scale = (real)vals[23]; b->translation_scale = (real)vals[24];
     if (mask) { b->mask = (int*)malloc(s->n * sizeof(int)); memcpy(b->mask, mask, s->n * sizeof(int)); }
 }
@@ -605,7 +606,8 @@ void mpmref_stress_of_F(sim_t* s, int p) { compute_stress(s, p, (real)1e-4); }
 
 /* one p2g2p (mpm_solver_warp.py:514-637) */
 static void substep(sim_t* s, double dt_d) {
-    const real dt = (real)dt_d, time = (real)s->time;
+    const real dt = (real)dt_d;
+    const float time = (float)s->time;      /* wp kernels receive `time` as fp32 */
     const int n = s->n;
     const size_t nodes = (size_t)s->n_grid * s->n_grid * s->n_grid;
     memset(s->grid_m, 0, nodes * sizeof(real));

@@ -163,23 +163,8 @@ class MpmRef:
         return int(self.lib.mpmref_num_threads())
 
 
-# --------------------------------------------------------------------------------------------------
-# Synthetic scene of BASELINE config 3: uniform particles in [0.6,1.4]^3 of a
-# grid_lim = 2 box, vol = dx^3 / count_in_cell (PhysGaussian particle_filling/filling.py:247-288),
-# per-particle E / nu / density in the U-Net field's post-unscale ranges, jelly + optional others.
-# --------------------------------------------------------------------------------------------------
-def synthetic_scene(n: int, n_grid: int, grid_lim: float = 2.0, seed: int = 0, materials: Sequence[int] = (0,),
-                    lo: float = 0.6, hi: float = 1.4):
-    rng = np.random.default_rng(seed)
-    x = rng.uniform(lo, hi, size=(n, 3)).astype(np.float32)
-    dx = grid_lim / n_grid
-    cell = np.floor(x / dx).astype(np.int64)
-    key = (cell[:, 0] * n_grid + cell[:, 1]) * n_grid + cell[:, 2]
-    _, inv, cnt = np.unique(key, return_inverse=True, return_counts=True)
-    vol = (dx ** 3 / cnt[inv]).astype(np.float32)
-    density = rng.uniform(200.0, 2000.0, size=n).astype(np.float32)
-    E = (10.0 ** rng.uniform(4.0, 6.5, size=n)).astype(np.float32)
-    nu = rng.uniform(0.21, 0.45, size=n).astype(np.float32)
-    material = np.asarray(materials, dtype=np.int32)[rng.integers(0, len(materials), size=n)]
-    v = (0.1 * rng.standard_normal((n, 3))).astype(np.float32)
-    return dict(x=x, v=v, vol=vol, density=density, E=E, nu=nu, material=material)
+# Synthetic scene of BASELINE config 3: shared with bench.py, lives with the other synthetic-data
+# generators (pure numpy, no solver arithmetic).
+import sys as _sys
+_sys.path.insert(0, os.path.dirname(_HERE))
+from pixie_b200.synthetic import synthetic_scene  # noqa: E402,F401

@@ -59,6 +59,8 @@ _SIGNATURES = {
     "pixie_unet_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "pixie_unet_forward_ncdhw": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "pixie_unet_forward_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "pixie_unet_profile": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_double), C.c_int]),
+    "pixie_pack_predictions": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p]),
     "pixie_unet_launch_count": (C.c_int, [C.c_void_p]),
     "pixie_unet_check": (C.c_int, [C.c_void_p]),
     "pixie_unet_flops": (C.c_double, [C.c_void_p]),

@@ -2,6 +2,7 @@
 #include "../../include/pixie_b200.h"
 #include "mpm.cuh"
 #include "unet.cuh"
+#include "unet_kernels.cuh"
 
 #include <string>
 
@@ -64,6 +65,18 @@ int pixie_unet_forward_ncdhw(pixie_unet_t h, const float* feat, int batch, float
 int pixie_unet_forward_host(pixie_unet_t h, const void* feat, int batch, float* out, void* stream) {
     if (!h || !feat || !out) return set_err("null argument");
     if (pixie::unet_forward_host(h->u, feat, batch, out, (cudaStream_t)stream)) return set_err(pixie::unet_error(h->u));
+    return 0;
+}
+int pixie_unet_profile(pixie_unet_t h, const void* feat, int batch, float* out, void* stream, float* ms, int* kinds, double* flops, int cap) {
+    if (!h || !feat || !out || !ms || !kinds || !flops) { set_err("null argument"); return -1; }
+    const int n = pixie::unet_profile(h->u, feat, batch, out, (cudaStream_t)stream, ms, kinds, flops, cap);
+    if (n < 0) set_err(pixie::unet_error(h->u));
+    return n;
+}
+int pixie_pack_predictions(const float* seg_logits_dev, const float* cont_dev, float* out_dev, int batch, int64_t voxels, int n_classes, void* stream) {
+    if (!seg_logits_dev || !cont_dev || !out_dev) return set_err("null argument");
+    if (require_device()) return 1;
+    if (pixie::launch_pack_predictions(seg_logits_dev, cont_dev, out_dev, batch, voxels, n_classes, (cudaStream_t)stream)) return set_err("launch failed");
     return 0;
 }
 int pixie_unet_launch_count(pixie_unet_t h) { return h ? pixie::unet_launch_count(h->u) : 0; }

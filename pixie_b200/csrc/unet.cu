@@ -52,6 +52,8 @@ struct UNet {
 
     std::vector<void*> allocs;
     std::vector<std::function<int(cudaStream_t)>> ops;   // bound to the batch size in `cur_nb`
+    std::vector<int> op_kinds;                            // PIXIE_OP_* per op
+    std::vector<double> op_flops;                         // algorithmic FLOPs per op (convs only)
     std::vector<std::unique_ptr<ConvOp>> convs;
     std::map<std::string, DevT> named;
     int* d_err = nullptr;
@@ -131,6 +133,7 @@ struct Builder {
         const int V = (int)vox(x.sp), C = x.C;
         const float* xp = x.p;
         u.ops.push_back([=](cudaStream_t st) { return launch_moments(xp, up->cur_nb, V, C, stats, st); });
+        u.op_kinds.push_back(PIXIE_OP_MOMENTS); u.op_flops.push_back(0);
     }
 
     // normalise x (LN with per-voxel affine, or GN) into channel slice [c0, c0+x.C) of dst;
@@ -144,6 +147,7 @@ struct Builder {
         if (raw) { a.raw_dst = raw->hi; a.raw_lo = raw->lo; a.raw_ld = raw->C; a.raw_c0 = raw_c0; }
         UNet* up = &u;
         u.ops.push_back([=](cudaStream_t st) { return launch_norm_act(a, up->cur_nb, st); });
+        u.op_kinds.push_back(PIXIE_OP_NORM); u.op_flops.push_back(0);
     }
 
     struct ConvIn { F16 t; int ks; int cin_real; std::string wname; };
@@ -152,6 +156,7 @@ struct Builder {
     ConvOp* emit_conv(const std::vector<ConvIn>& ins, int sp_out, int stride, int Cout, const float* residual,
                       float* out, bool planar, const std::vector<std::string>& bias_names) {
         auto op = std::make_unique<ConvOp>();
+        const double flops_before = u.flops;
         ConvDesc& d = op->desc;
         d.NB = NB; d.D = d.H = d.W = sp_out; d.stride = stride; d.Cout = Cout;
         d.Cout_pad = (Cout + 15) / 16 * 16;
@@ -208,6 +213,7 @@ struct Builder {
             pl.grid = items < pl.grid ? items : pl.grid;
             return conv_plan_launch(pl, st);
         });
+        u.op_kinds.push_back(PIXIE_OP_CONV); u.op_flops.push_back(u.flops - flops_before);
         u.convs.push_back(std::move(op));
         return raw;
     }
@@ -276,6 +282,7 @@ struct Builder {
             UNet* upn = &u;
             const float* xp = x.p; __half* hi = up.hi; __half* lo = up.lo; const int sp = x.sp, C = x.C;
             u.ops.push_back([=](cudaStream_t st) { return launch_upsample2(xp, hi, lo, upn->cur_nb, sp, C, st); });
+            u.op_kinds.push_back(PIXIE_OP_UPSAMPLE); u.op_flops.push_back(0);
         }
         DevT out = alloc_f32(x.C, 2 * x.sp, path);
         if (!emit_conv({{up, 3, x.C, path + ".conv.weight"}}, 2 * x.sp, 1, x.C, nullptr, out.p, false, {path + ".conv.bias"})) return {};
@@ -298,6 +305,7 @@ struct Builder {
             UNet* upn = &u;
             const float* qp = qkv.p; __half* hi = at.hi; __half* lo = at.lo;
             u.ops.push_back([=](cudaStream_t s) { return launch_attention(qp, hi, lo, upn->cur_nb, T, C, s); });
+            u.op_kinds.push_back(PIXIE_OP_ATTENTION); u.op_flops.push_back(0);
         }
         DevT out = alloc_f32(C, x.sp, path);
         if (!emit_conv({{at, 1, C, path + ".proj_out.weight"}}, x.sp, 1, C, x.p, out.p, false, {path + ".proj_out.bias"})) return {};
@@ -492,6 +500,30 @@ int unet_forward(UNet* u, const void* feat_f16, int batch, float* out, cudaStrea
     }
     u->head_conv->plan.p.out = out;
     return run_ops(u, batch, st);
+}
+
+int unet_profile(UNet* u, const void* feat_f16, int batch, float* out, cudaStream_t st, float* ms, int* kinds, double* flops, int cap) {
+    if (!u->finalized) { u->error = "profile before finalize"; return -1; }
+    const int n = (int)u->ops.size();
+    if (cap < n) { u->error = "profile: buffers too small"; return -1; }
+    if (unet_forward(u, feat_f16, batch, out, st)) return -1;      // warm + retarget
+    std::vector<cudaEvent_t> ev(n + 1);
+    for (auto& e : ev) cudaEventCreate(&e);
+    u->cur_nb = batch;
+    cudaMemsetAsync(u->d_stats, 0, u->stats_doubles * sizeof(double), st);
+    cudaEventRecord(ev[0], st);
+    for (int i = 0; i < n; ++i) {
+        if (u->ops[i](st)) { u->error = "kernel launch failed"; return -1; }
+        cudaEventRecord(ev[i + 1], st);
+    }
+    cudaStreamSynchronize(st);
+    for (int i = 0; i < n; ++i) {
+        cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]);
+        kinds[i] = u->op_kinds[i];
+        flops[i] = u->op_flops[i];
+    }
+    for (auto& e : ev) cudaEventDestroy(e);
+    return n;
 }
 
 int unet_forward_ncdhw(UNet* u, const float* feat_f32, int batch, float* out, cudaStream_t st) {

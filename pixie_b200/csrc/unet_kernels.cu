@@ -220,7 +220,33 @@ ncdhw_to_ndhwc_f16_kernel(const float* __restrict__ x, __half* __restrict__ y, i
     y[(size_t)nb * V * Cpad + i] = __float2half_rn(val);
 }
 
+// save_predictions packing (inference_combined.py:173-199): out[0:3] = continuous prediction,
+// out[3 + c] = (argmax_c seg_logits == c) as float, c in [0, n_classes); all planar (C, D, H, W).
+__global__ void __launch_bounds__(256)
+pack_predictions_kernel(const float* __restrict__ seg, const float* __restrict__ cont, float* __restrict__ out,
+                        long long V, int n_classes) {
+    const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int nb = blockIdx.y;
+    if (v >= V) return;
+    const float* sp = seg + (size_t)nb * n_classes * V;
+    int best = 0;
+    float bv = sp[v];
+    for (int c = 1; c < n_classes; ++c) {           // torch.argmax returns the first maximal index
+        const float x = sp[(size_t)c * V + v];
+        if (x > bv) { bv = x; best = c; }
+    }
+    float* op = out + (size_t)nb * (3 + n_classes) * V;
+    for (int c = 0; c < 3; ++c) op[(size_t)c * V + v] = cont[((size_t)nb * 3 + c) * V + v];
+    for (int c = 0; c < n_classes; ++c) op[(size_t)(3 + c) * V + v] = (c == best) ? 1.f : 0.f;
+}
+
 // ------------------------------------------------------------------------------------ launchers
+int launch_pack_predictions(const float* seg, const float* cont, float* out, int NB, long long V, int n_classes, cudaStream_t st) {
+    dim3 grid((unsigned)((V + 255) / 256), NB);
+    pack_predictions_kernel<<<grid, 256, 0, st>>>(seg, cont, out, V, n_classes);
+    return (int)cudaGetLastError();
+}
+
 static inline int vox_per_block_for(int V) { return V >= 4096 ? 256 : 64; }
 
 int launch_moments(const float* x, int NB, int V, int C, double* stats, cudaStream_t st) {

@@ -31,6 +31,7 @@ int launch_moments(const float* x, int NB, int V, int C, double* stats, cudaStre
 int launch_norm_act(NormArgs a, int NB, cudaStream_t st);
 int launch_upsample2(const float* x, __half* y, __half* ylo, int NB, int sp, int C, cudaStream_t st);
 int launch_attention(const float* qkv, __half* out, __half* out_lo, int NB, int T, int C, cudaStream_t st);
+int launch_pack_predictions(const float* seg, const float* cont, float* out, int NB, long long V, int n_classes, cudaStream_t st);
 int launch_ncdhw_to_ndhwc_f16(const float* x, __half* y, int NB, int C, int Cpad, long long V, cudaStream_t st);
 
 }  // namespace pixie

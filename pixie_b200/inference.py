@@ -1,0 +1,70 @@
+"""Host-side mirror of the reference's inference hot loop
+(third_party/Wavelet-Generation/trainer/inference_combined.py): create_models (:81-105),
+process_batch's forward + argmax (:122-126) and save_predictions' (3 + n_classes, D, H, W) packing
+(:173-199) — without the metrics / file I/O, which stay outside the hot path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from .unet import RegressionUNet, SegmentationUNet
+
+
+class MaterialFieldPredictor:
+    """seg_network + cont_network resident on one GPU; one H2D of the voxel grid serves both."""
+
+    def __init__(self, feature_channels: int, cond_dim: int = 32, model_channels: int = 64, num_res_blocks: int = 3,
+                 channel_mult: Tuple[int, ...] = (1, 1, 2, 4), attention_resolutions: Tuple[int, ...] = (),
+                 grid_size: int = 64, num_material_classes: int = 8, device="cuda:0", max_batch: int = 1,
+                 precision: str = "fp16x3"):
+        kw = dict(feature_channels=feature_channels, cond_dim=cond_dim, model_channels=model_channels,
+                  num_res_blocks=num_res_blocks, channel_mult=channel_mult, attention_resolutions=attention_resolutions,
+                  grid_size=grid_size, max_batch=max_batch, precision=precision)
+        self.seg_network = SegmentationUNet(num_classes=num_material_classes, **kw).to(device)
+        self.cont_network = RegressionUNet(out_channels=3, **kw).to(device)
+        self.device = torch.device(device)
+        self.grid_size, self.feature_channels = grid_size, feature_channels
+        self.n_classes, self.max_batch = num_material_classes, max_batch
+        self._feat_dev: Optional[torch.Tensor] = None
+        self._packed_dev: Optional[torch.Tensor] = None
+
+    def load_state_dicts(self, seg_sd, cont_sd, strict: bool = True):
+        self.seg_network.load_state_dict(seg_sd, strict=strict)
+        self.cont_network.load_state_dict(cont_sd, strict=strict)
+        return self
+
+    def predict(self, feat_ndhwc_f16: torch.Tensor):
+        """Device fp16 (N, D, H, W, C) -> (seg_logits (N, n_classes, D,H,W), cont_pred (N, 3, D,H,W)) fp32."""
+        return (self.seg_network.forward_channels_last_f16(feat_ndhwc_f16),
+                self.cont_network.forward_channels_last_f16(feat_ndhwc_f16))
+
+    def pack(self, seg_logits: torch.Tensor, cont_pred: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """(N, 3 + n_classes, D, H, W): continuous channels + one-hot argmax, as sample_*_pred.npy."""
+        n, G = seg_logits.shape[0], self.grid_size
+        if out is None:
+            out = torch.empty((n, 3 + self.n_classes, G, G, G), dtype=torch.float32, device=self.device)
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(_lib.load().pixie_pack_predictions(C.c_void_p(seg_logits.data_ptr()), C.c_void_p(cont_pred.data_ptr()),
+                                                      C.c_void_p(out.data_ptr()), n, G ** 3, self.n_classes, C.c_void_p(st)))
+        return out
+
+    def predict_packed_host(self, feat_pinned: torch.Tensor, out_pinned: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """End to end with HOST buffers: pinned fp16 (N, D, H, W, C) -> pinned fp32 (N, 3+n_classes, D,H,W).
+        One H2D copy of the grid, both networks, packing, one D2H copy; returns after the stream syncs."""
+        n, G = feat_pinned.shape[0], self.grid_size
+        if self._feat_dev is None or self._feat_dev.shape[0] < n:
+            self._feat_dev = torch.empty((max(n, self.max_batch), G, G, G, self.feature_channels), dtype=torch.float16, device=self.device)
+            self._packed_dev = torch.empty((max(n, self.max_batch), 3 + self.n_classes, G, G, G), dtype=torch.float32, device=self.device)
+        if out_pinned is None:
+            out_pinned = torch.empty((n, 3 + self.n_classes, G, G, G), dtype=torch.float32).pin_memory()
+        with torch.cuda.device(self.device):
+            self._feat_dev[:n].copy_(feat_pinned, non_blocking=True)
+            seg, cont = self.predict(self._feat_dev[:n])
+            self.pack(seg, cont, self._packed_dev[:n])
+            out_pinned.copy_(self._packed_dev[:n], non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        return out_pinned

@@ -268,6 +268,24 @@ class _B200UNet:
         self._ensure_built()
         return float(_lib.load().pixie_unet_flops(self._handle))
 
+    def profile(self, feat_ndhwc: torch.Tensor):
+        """Per-launch device times of one forward: list of (kind, ms, algorithmic_flops)."""
+        self._ensure_built()
+        lib = _lib.load()
+        G = self.grid_size
+        n = feat_ndhwc.shape[0]
+        out = torch.empty((n, self.out_channels, G, G, G), dtype=torch.float32, device=self._device)
+        cap = 1024
+        ms, kinds, fl = (C.c_float * cap)(), (C.c_int * cap)(), (C.c_double * cap)()
+        with torch.cuda.device(self._device):
+            st = torch.cuda.current_stream().cuda_stream
+            k = lib.pixie_unet_profile(self._handle, C.c_void_p(feat_ndhwc.data_ptr()), n, C.c_void_p(out.data_ptr()),
+                                       C.c_void_p(st), ms, kinds, fl, cap)
+        if k < 0:
+            raise _lib.PixieError(lib.pixie_last_error().decode())
+        names = {0: "conv", 1: "moments", 2: "norm", 3: "upsample", 4: "attention"}
+        return [(names[kinds[i]], ms[i], fl[i]) for i in range(k)]
+
     def debug_fetch(self, name: str, channels: int, sp: int, batch: int = 1) -> torch.Tensor:
         """Intermediate activation by reference module path, returned as (N, C, D, H, W) fp32 (CPU)."""
         buf = torch.empty(batch * sp ** 3 * channels, dtype=torch.float32)

@@ -1,0 +1,145 @@
+"""GPU parity tests of the MPM rollout (pytest -m gpu). Calls go through the C ABI via the
+MPM_Simulator_WARP shim; oracle/mpm_ref.c is the checker (fp32 build = the reference's precision;
+fp64 build = drift reference). Tolerances: positions 1e-5 after 200 substeps against the fp32 oracle
+(measured ~1e-6; the GPU scatter order differs, so bit-exactness is not defined for float atomics —
+the reference itself is run-to-run non-deterministic, mpm_utils.py:393-394)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import mpm_ref as R
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _pair(n, ng, materials, seed, prec="f32", bcs=True, g=(0.0, 0.0, -9.8), damping=0.9999):
+    from pixie_b200.mpm_solver_warp import MPM_Simulator_WARP
+    sc = R.synthetic_scene(n, ng, seed=seed, materials=materials)
+    s = MPM_Simulator_WARP(10)
+    s.load_initial_data_from_torch(torch.from_numpy(sc["x"]).to(DEV), torch.from_numpy(sc["vol"]).to(DEV), None, n_grid=ng, grid_lim=2.0)
+    s.set_parameters_dict({"material": "jelly", "g": list(g), "density": 1000.0, "E": 1e5, "nu": 0.3, "yield_stress": 2e3,
+                           "grid_v_damping_scale": damping, "rpic_damping": 0.0, "friction_angle": 30.0, "hardening": 1,
+                           "xi": 0.1, "softening": 0.1, "plastic_viscosity": 10.0, "bulk_modulus": 1e5})
+    s.mpm_model.E = torch.from_numpy(sc["E"]).to(DEV)
+    s.mpm_model.nu = torch.from_numpy(sc["nu"]).to(DEV)
+    s.mpm_state.particle_material = torch.from_numpy(sc["material"]).to(DEV)
+    s.reset_densities_and_update_masses(torch.from_numpy(sc["density"]).to(DEV))
+    s.import_particle_v_from_torch(torch.from_numpy(sc["v"]).to(DEV))
+    s.finalize_mu_lam()
+    o = R.MpmRef(n, ng, 2.0, prec)
+    for k, f in (("x", "X"), ("v", "V"), ("vol", "VOL"), ("density", "DENSITY"), ("E", "E"), ("nu", "NU"), ("material", "MATERIAL")):
+        o.set(f, sc[k])
+    o.set("YIELD", np.full(n, 2e3)); o.set("BULK", np.full(n, 1e5))
+    o.compute_mass(); o.compute_mu_lam()
+    o.set_params(g=g, grid_v_damping_scale=damping, rpic_damping=0.0, alpha=R.friction_alpha(30.0), hardening=1, xi=0.1,
+                 softening=0.1, plastic_viscosity=10.0)
+    if bcs:
+        s.add_bounding_box(); o.add_bc(R.BC_BBOX)
+        s.set_velocity_on_cuboid(point=[1.0, 1.0, 0.62], size=[0.5, 0.5, 0.04], velocity=[0, 0, 0])
+        o.add_bc(R.BC_CUBOID, point=[1.0, 1.0, 0.62], size=[0.5, 0.5, 0.04])
+        s.set_velocity_on_cuboid(point=[0.7, 1.0, 1.3], size=[0.05, 0.2, 0.05], velocity=[0.5, 0, 0], start_time=0.0, end_time=0.01, reset=1)
+        o.add_bc(R.BC_CUBOID, point=[0.7, 1.0, 1.3], size=[0.05, 0.2, 0.05], velocity=[0.5, 0, 0], end_time=0.01, reset=1)
+        s.add_surface_collider(point=[1.0, 1.0, 0.1], normal=[0, 0, 2], surface="sticky", friction=0.0, start_time=0.0, end_time=1e3)
+        o.add_bc(R.BC_SURFACE, point=[1.0, 1.0, 0.1], normal=[0, 0, 1], end_time=1e3)
+        p, sz = np.float32([1.0, 1.0, 1.2]), np.float32([0.2, 0.2, 0.1])
+        mask = (np.abs(sc["x"] - p) < sz).all(1).astype(np.int32)
+        s.add_impulse_on_particles(force=[0.05, 0.0, -0.02], dt=1e-4, point=list(p), size=list(sz), num_dt=20, start_time=0.0)
+        o.add_bc(R.BC_IMPULSE, velocity=[0.05, 0.0, -0.02], start_time=0.0, end_time=0.0 + 1e-4 * 20, mask=mask)
+        assert (s._masks[-1].cpu().numpy() == mask).all()                      # selection_add_impulse_on_particles
+        p2, s2 = np.float32([1.3, 1.3, 0.9]), np.float32([0.1, 0.1, 0.1])
+        mask2 = (np.abs(sc["x"] - p2) < s2).all(1).astype(np.int32)
+        s.enforce_particle_velocity_translation(point=list(p2), size=list(s2), velocity=[0, 0.2, 0], start_time=0.001, end_time=0.004)
+        o.add_bc(R.BC_VTRANS, velocity=[0, 0.2, 0], start_time=0.001, end_time=0.004, mask=mask2)
+    return s, o, sc
+
+
+def _err(s, o, fid):
+    a = s._t[fid].detach().cpu().numpy().astype(np.float64).reshape(s.n_particles, -1)
+    return np.abs(a - o.get(fid).reshape(s.n_particles, -1)).max()
+
+
+@pytest.mark.parametrize("materials", [(0,), (2,), (1,), (5,), (3,), (0, 1, 2, 3, 4, 5, 6)])
+def test_rollout_matches_fp32_oracle(built_lib, cuda_dev, materials):
+    s, o, _ = _pair(5000, 32, materials, seed=3)
+    s.p2g2p(0, 1e-4); o.step(1, 1e-4)
+    assert _err(s, o, "X") < 1e-7 and _err(s, o, "V") < 1e-5
+    s.p2g2p_n(199, 1e-4); o.step(199, 1e-4)
+    torch.cuda.synchronize()
+    assert _err(s, o, "X") < 1e-5
+    assert _err(s, o, "V") < 2e-3
+    assert _err(s, o, "F") < 5e-4 and _err(s, o, "F_TRIAL") < 5e-4
+    assert abs(s.time - o.time) < 1e-12 and abs(s.time - 0.02) < 1e-12       # device clock == host clock
+
+
+def test_rotation_modifier_and_cylinder_selection(built_lib, cuda_dev):
+    s, o, sc = _pair(4000, 32, (0,), seed=9, bcs=False)
+    point, normal, hhr = [1.0, 1.0, 1.0], [0.0, 0.0, 1.0], [0.2, 0.25]
+    s.enforce_particle_velocity_rotation(point=point, normal=normal, half_height_and_radius=hhr, rotation_scale=2.0,
+                                         translation_scale=0.1, start_time=0.0, end_time=0.005)
+    off = sc["x"].astype(np.float64) - np.array(point)
+    mask = ((np.abs(off[:, 2]) < hhr[0]) & (np.linalg.norm(off[:, :2], axis=1) < hhr[1])).astype(np.int32)
+    gm = s._masks[-1].cpu().numpy()
+    assert (gm != mask).sum() <= 2                                               # fp32 vs fp64 on the cylinder surface
+    n = np.float32([0, 0, 1]); h1 = np.float32([1, 1, 1]); h1 = h1 - np.dot(h1, n) * n; h1 = h1 / np.linalg.norm(h1); h2 = np.cross(h1, n)
+    o.add_bc(R.BC_VROT, point=point, normal=list(n), h1=list(h1), h2=list(h2), hhr=hhr, rotation_scale=2.0, translation_scale=0.1,
+             start_time=0.0, end_time=0.005, mask=gm)
+    s.p2g2p_n(60, 1e-4); o.step(60, 1e-4)
+    torch.cuda.synchronize()
+    assert gm.sum() > 20 and _err(s, o, "X") < 1e-5
+
+
+def test_setup_and_export_kernels(built_lib, cuda_dev):
+    s, o, sc = _pair(3000, 32, (0,), seed=5, bcs=False)
+    n = 3000
+    cov0 = np.abs(np.random.default_rng(0).standard_normal((n, 6))).astype(np.float32) * 1e-4
+    s.mpm_state.particle_init_cov = torch.from_numpy(cov0.reshape(-1)).to(DEV)
+    o.set("INIT_COV", cov0)
+    s.p2g2p_n(30, 1e-4); o.step(30, 1e-4)
+    cov = s.export_particle_cov_to_torch().cpu().numpy().reshape(n, 6)
+    o.compute_cov_from_F()
+    assert np.abs(cov - o.get("COV")).max() < 1e-8
+    Rm = s.export_particle_R_to_torch().cpu().numpy().reshape(n, 3, 3)
+    assert np.abs(np.einsum("nij,nkj->nik", Rm, Rm) - np.eye(3)).max() < 1e-5  # rotations
+    assert np.abs(np.linalg.det(Rm) - 1).max() < 1e-5
+    mu = s.mpm_model.mu.numpy(); lam = s.mpm_model.lam.numpy()
+    E, nu = sc["E"].astype(np.float64), sc["nu"].astype(np.float64)
+    assert np.allclose(mu, E / (2 * (1 + nu)), rtol=1e-6) and np.allclose(lam, E * nu / ((1 + nu) * (1 - 2 * nu)), rtol=1e-5)
+    # apply_additional_params: the per-particle boxes of material_field._apply_material_properties_to_solver
+    pos = s.mpm_state.particle_x.numpy()
+    newE = np.linspace(1e4, 2e4, n).astype(np.float32)
+    s.set_parameters_dict({"additional_material_params": [
+        {"point": pos[i].tolist(), "size": [1e-5, 1e-5, 1e-5], "density": 500.0 + i, "E": float(newE[i]), "nu": 0.25, "material": "sand" if i % 2 else 0}
+        for i in range(n)]})
+    assert np.allclose(s.mpm_model.E.numpy(), newE) and (s.mpm_state.particle_material.numpy() == (np.arange(n) % 2) * 2).all()
+    assert np.allclose(s.mpm_state.particle_mass.numpy(), (500.0 + np.arange(n)) * sc["vol"], rtol=1e-6)
+    with pytest.raises(TypeError):
+        s.set_parameters_dict({"material": "fluid"})                              # excluded name -> -1 -> TypeError (:312-313)
+    with pytest.raises(ValueError):
+        s.add_surface_collider([0, 0, 0], [0, 0, 1], surface="sticky", friction=0.3)
+
+
+def test_conservation_at_full_size(built_lib, cuda_dev):
+    """BASELINE config 3 size (100k particles, 64^3): size-independent properties instead of the oracle.
+    Without gravity, damping or BCs the APIC transfer conserves linear momentum; grid mass equals
+    particle mass after p2g."""
+    s, _, sc = _pair(100_000, 64, (0,), seed=0, bcs=False, g=(0.0, 0.0, 0.0), damping=1.1)
+    m = s.mpm_state.particle_mass.numpy().astype(np.float64)
+    p0 = (m[:, None] * s.mpm_state.particle_v.numpy()).sum(0)
+    s.p2g2p_n(100, 1e-4)
+    torch.cuda.synchronize()
+    p1 = (m[:, None] * s.mpm_state.particle_v.numpy()).sum(0)
+    assert np.abs(p1 - p0).max() < 2e-4 * np.abs(m[:, None] * sc["v"]).sum()
+    x = s.mpm_state.particle_x.numpy()
+    assert np.isfinite(x).all() and x.min() > 0.5 and x.max() < 1.5
+
+
+def test_drift_vs_fp64_oracle(built_lib, cuda_dev):
+    """Position drift against the fp64 oracle over a rollout, next to the fp32-oracle noise floor."""
+    s, o64, _ = _pair(20_000, 48, (0,), seed=1, prec="f64")
+    _, o32, _ = _pair(20_000, 48, (0,), seed=1, prec="f32")
+    s.p2g2p_n(300, 1e-4); o64.step(300, 1e-4); o32.step(300, 1e-4)
+    torch.cuda.synchronize()
+    drift = _err(s, o64, "X")
+    floor = np.abs(o32.get("X") - o64.get("X")).max()
+    assert drift < 1e-4 and drift < 20 * floor + 1e-6
