@@ -26,6 +26,29 @@ struct SmemCtrl {
     int abort_flag;
 };
 
+constexpr int kStatsMaxC = 256;
+// per epilogue warp: [2][kStatsMaxC] floats (sum, sum of squares), private to the warp -> no atomics
+constexpr int kStatsSmemBytes = 4 * 2 * kStatsMaxC * 4;
+
+// Reduces v[0..15] (16 channels held by every lane = one voxel row each) over the 32 lanes of the warp.
+// Returns, in every lane, the column sum of channel stats_channel_of_lane(lane). 16 shuffles.
+__device__ __forceinline__ float warp_colsum16(float (&v)[16], int lane) {
+#pragma unroll
+    for (int half = 8, off = 16; half >= 1; half >>= 1, off >>= 1) {
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+            const float keep = up ? v[i + half] : v[i];
+            const float send = up ? v[i] : v[i + half];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+__device__ __forceinline__ int stats_channel_of_lane(int lane) {
+    return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+}
+
 struct TileCoord {
     int nb, d0, h0, w0, n0, ph_begin, ph_end, split, tde;
 };
@@ -63,6 +86,7 @@ conv3d_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
     uint8_t* w_smem = smem;
     uint8_t* s_smem = smem + (size_t)p.w_stages * p.w_stage_bytes;
     SmemCtrl* ctl = reinterpret_cast<SmemCtrl*>(s_smem + (size_t)p.s_stages * p.s_stage_bytes);
+    float* stats_sm = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ctl) + 512);   // used iff p.stats
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -93,88 +117,99 @@ conv3d_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
     volatile int* abort_flag = &ctl->abort_flag;
 
     if (warp == 0) {
-        // ================================================================ TMA producer
-        if (lane == 0) {
-            int ws = 0, wph = 0, ss = 0, sph = 0;
-            bool ok = true;
-            for (int wi = blockIdx.x; wi < total_items && ok; wi += gridDim.x) {
-                const TileCoord t = decode_tile(p, wi);
-                for (int ph = t.ph_begin; ph < t.ph_end && ok; ++ph) {
-                    const ConvPhase P = p.phases[ph];
-                    const int ntaps = P.n_kh * P.n_kd;
-                    ok = mbar_wait(&ctl->wempty[ws], wph ^ 1, abort_flag);
-                    if (!ok) break;
+        // ================================================================ TMA producer (warp-uniform, one elected lane issues)
+        int ws = 0, wph = 0, ss = 0, sph = 0;
+        bool ok = true;
+        for (int wi = blockIdx.x; wi < total_items && ok; wi += gridDim.x) {
+            const TileCoord t = decode_tile(p, wi);
+            for (int ph = t.ph_begin; ph < t.ph_end && ok; ++ph) {
+                const ConvPhase P = p.phases[ph];
+                const int ntaps = P.n_kh * P.n_kd;
+                ok = mbar_wait(&ctl->wempty[ws], wph ^ 1, abort_flag);
+                if (!ok) break;
+                if (elect_one()) {
                     mbar_expect_tx(&ctl->wfull[ws], (uint32_t)(ntaps * p.block_n * 128));
                     uint8_t* wdst = w_smem + (size_t)ws * p.w_stage_bytes;
                     for (int tap = 0; tap < ntaps; ++tap)
                         tma_load_2d(wdst + (size_t)tap * p.block_n * 128, &p.tmB, &ctl->wfull[ws],
                                     (P.wtile_base + tap) * 64, t.n0);
-                    if (++ws == p.w_stages) { ws = 0; wph ^= 1; }
+                }
+                if (++ws == p.w_stages) { ws = 0; wph ^= 1; }
 
-                    const int nplanes = t.tde + P.n_kd - 1;
-                    const uint32_t slab_bytes = (uint32_t)p.slab_rows[P.src] * 128u;
-                    for (int pl = 0; pl < nplanes && ok; ++pl) {
-                        ok = mbar_wait(&ctl->sempty[ss], sph ^ 1, abort_flag);
-                        if (!ok) break;
+                const int nplanes = t.tde + P.n_kd - 1;
+                const uint32_t slab_bytes = (uint32_t)p.slab_rows[P.src] * 128u;
+                for (int pl = 0; pl < nplanes && ok; ++pl) {
+                    ok = mbar_wait(&ctl->sempty[ss], sph ^ 1, abort_flag);
+                    if (!ok) break;
+                    if (elect_one()) {
                         mbar_expect_tx(&ctl->sfull[ss], slab_bytes);
                         tma_load_5d(s_smem + (size_t)ss * p.s_stage_bytes, &p.tmA[P.src],
                                     &ctl->sfull[ss], (int)P.c0, t.w0 * p.stride + P.dw,
                                     t.h0 * p.stride + P.dh0, (t.d0 + pl) * p.stride + P.dd0, t.nb);
-                        if (++ss == p.s_stages) { ss = 0; sph ^= 1; }
                     }
+                    if (++ss == p.s_stages) { ss = 0; sph ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
         // ================================================================ MMA issuer
-        if (lane == 0) {
-            int ws = 0, wph = 0, ss = 0, sph = 0, as = 0, aph = 0;
-            const uint32_t idesc = make_idesc_f16(128, (uint32_t)p.block_n);
-            const uint64_t hi_xor = p.desc_xor;
-            bool ok = true;
-            for (int wi = blockIdx.x; wi < total_items && ok; wi += gridDim.x) {
-                const TileCoord t = decode_tile(p, wi);
-                ok = mbar_wait(&ctl->tempty[as], aph ^ 1, abort_flag);
+        // The whole warp runs this loop with warp-uniform control flow (so the compiler keeps descriptors
+        // and addresses in uniform registers); only the tcgen05 instructions themselves are issued by one
+        // elected lane. A single divergent thread costs ~25 scalar instructions per MMA (ncu: tensor pipe
+        // 23 % busy, issue thread never waiting).
+        int ws = 0, wph = 0, ss = 0, sph = 0, as = 0, aph = 0;
+        const uint32_t idesc = make_idesc_f16(128, (uint32_t)p.block_n);
+        const uint64_t desc_fixed = (make_sw128_desc(0, 1024) ^ p.desc_xor);   // everything but the start address
+        const uint32_t w_base0 = smem_u32(w_smem), s_base0 = smem_u32(s_smem);
+        const uint32_t kh_stride16 = (uint32_t)(p.TW * 128) >> 4;             // descriptor units of 16 B
+        const uint32_t tap_stride16 = (uint32_t)(p.block_n * 128) >> 4;
+        bool ok = true;
+        for (int wi = blockIdx.x; wi < total_items && ok; wi += gridDim.x) {
+            const TileCoord t = decode_tile(p, wi);
+            ok = mbar_wait(&ctl->tempty[as], aph ^ 1, abort_flag);
+            if (!ok) break;
+            tc_fence_after();
+            uint32_t touched = 0;
+            for (int ph = t.ph_begin; ph < t.ph_end && ok; ++ph) {
+                const ConvPhase P = p.phases[ph];
+                const int n_kd = P.n_kd, n_kh = P.n_kh;
+                ok = mbar_wait(&ctl->wfull[ws], wph, abort_flag);
                 if (!ok) break;
-                tc_fence_after();
-                uint32_t touched = 0;
-                for (int ph = t.ph_begin; ph < t.ph_end && ok; ++ph) {
-                    const ConvPhase P = p.phases[ph];
-                    ok = mbar_wait(&ctl->wfull[ws], wph, abort_flag);
+                const uint32_t w16 = (w_base0 + (uint32_t)(ws * p.w_stage_bytes)) >> 4;
+                const int nplanes = t.tde + n_kd - 1;
+                for (int pl = 0; pl < nplanes && ok; ++pl) {
+                    ok = mbar_wait(&ctl->sfull[ss], sph, abort_flag);
                     if (!ok) break;
-                    const uint32_t w_addr = smem_u32(w_smem + (size_t)ws * p.w_stage_bytes);
-                    const int nplanes = t.tde + P.n_kd - 1;
-                    for (int pl = 0; pl < nplanes && ok; ++pl) {
-                        ok = mbar_wait(&ctl->sfull[ss], sph, abort_flag);
-                        if (!ok) break;
-                        tc_fence_after();
-                        const uint32_t s_addr = smem_u32(s_smem + (size_t)ss * p.s_stage_bytes);
-                        for (int kd = 0; kd < P.n_kd; ++kd) {
-                            const int d = pl - kd;
-                            if (d < 0 || d >= t.tde) continue;
-                            const uint32_t acc = tmem_base + (uint32_t)((as * p.TD + d) * p.block_n);
-                            for (int kh = 0; kh < P.n_kh; ++kh) {
-                                const int tap = kd * P.n_kh + kh;
-                                const uint32_t a_base = s_addr + (uint32_t)(kh * p.TW * 128);
-                                const uint32_t b_base = w_addr + (uint32_t)(tap * p.block_n * 128);
-#pragma unroll
-                                for (int k4 = 0; k4 < 4; ++k4) {
-                                    const uint64_t da = make_sw128_desc(a_base + k4 * 32, 1024) ^ hi_xor;
-                                    const uint64_t db = make_sw128_desc(b_base + k4 * 32, 1024) ^ hi_xor;
-                                    umma_f16(acc, da, db, idesc, (touched >> d) & 1u);
-                                    touched |= (1u << d);
-                                }
+                    tc_fence_after();
+                    const uint32_t s16 = (s_base0 + (uint32_t)(ss * p.s_stage_bytes)) >> 4;
+                    for (int kd = 0; kd < n_kd; ++kd) {
+                        const int d = pl - kd;
+                        if (d < 0 || d >= t.tde) continue;
+                        const uint32_t acc = tmem_base + (uint32_t)((as * p.TD + d) * p.block_n);
+                        uint32_t first = ((touched >> d) & 1u) ^ 1u;          // 1: this accumulator is still empty
+                        touched |= (1u << d);
+                        for (int kh = 0; kh < n_kh; ++kh) {
+                            const uint64_t da = desc_fixed | (uint64_t)((s16 + (uint32_t)kh * kh_stride16) & 0x3FFFu);
+                            const uint64_t db = desc_fixed | (uint64_t)((w16 + (uint32_t)(kd * n_kh + kh) * tap_stride16) & 0x3FFFu);
+                            if (elect_one()) {
+                                // 4 x (128 x N x 16) MMAs: K advances by 32 B = 2 descriptor units inside the swizzle atom
+                                umma_f16(acc, da, db, idesc, first ^ 1u);
+                                umma_f16(acc, da + 2, db + 2, idesc, 1u);
+                                umma_f16(acc, da + 4, db + 4, idesc, 1u);
+                                umma_f16(acc, da + 6, db + 6, idesc, 1u);
                             }
+                            first = 0;
                         }
-                        umma_commit(&ctl->sempty[ss]);   // slab slot free once these MMAs retire
-                        if (++ss == p.s_stages) { ss = 0; sph ^= 1; }
                     }
-                    umma_commit(&ctl->wempty[ws]);
-                    if (++ws == p.w_stages) { ws = 0; wph ^= 1; }
+                    if (elect_one()) umma_commit(&ctl->sempty[ss]);   // slab slot free once these MMAs retire
+                    if (++ss == p.s_stages) { ss = 0; sph ^= 1; }
                 }
-                umma_commit(&ctl->tfull[as]);             // accumulators complete
-                if (++as == p.acc_sets) { as = 0; aph ^= 1; }
+                if (elect_one()) umma_commit(&ctl->wempty[ws]);
+                if (++ws == p.w_stages) { ws = 0; wph ^= 1; }
             }
+            if (elect_one()) umma_commit(&ctl->tfull[as]);            // accumulators complete
+            __syncwarp();
+            if (++as == p.acc_sets) { as = 0; aph ^= 1; }
         }
     } else {
         // ================================================================ epilogue (warps 2..5)
@@ -184,11 +219,40 @@ conv3d_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
         int as = 0, aph = 0;
         bool ok = true;
         const long long DHW = (long long)p.D * p.H * p.W;
+        const bool do_stats = p.stats != nullptr;
+        float* my_stats = stats_sm + (size_t)(warp - 2) * 2 * kStatsMaxC;
+        const int et = threadIdx.x - 64;        // 0..127 among the epilogue threads
+        int stats_nb = -1;
+        if (do_stats) {
+            for (int i = lane; i < 2 * kStatsMaxC; i += 32) my_stats[i] = 0.f;
+            __syncwarp();
+        }
+        auto flush_stats = [&](int nb) {
+            // all 4 epilogue warps: fold the warp-private partial sums into the global fp64 accumulators
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            for (int ch = et; ch < p.Cout; ch += 128) {
+                float s = 0.f, qq = 0.f;
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+                    s += stats_sm[(size_t)w * 2 * kStatsMaxC + ch];
+                    qq += stats_sm[(size_t)w * 2 * kStatsMaxC + kStatsMaxC + ch];
+                }
+                atomicAdd(p.stats + ((size_t)nb * p.Cout + ch) * 2, (double)s);
+                atomicAdd(p.stats + ((size_t)nb * p.Cout + ch) * 2 + 1, (double)qq);
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            for (int i = lane; i < 2 * kStatsMaxC; i += 32) my_stats[i] = 0.f;
+            __syncwarp();
+        };
         for (int wi = blockIdx.x; wi < total_items && ok; wi += gridDim.x) {
             const TileCoord t = decode_tile(p, wi);
             ok = mbar_wait(&ctl->tfull[as], aph, abort_flag);
             if (!ok) break;
             tc_fence_after();
+            if (do_stats && stats_nb != t.nb) {
+                if (stats_nb >= 0) flush_stats(stats_nb);
+                stats_nb = t.nb;
+            }
             const int hh = t.h0 + th, ww = t.w0 + tw;
             const bool row_ok = (hh < p.H) && (ww < p.W);
             const bool first_split = (t.split == 0);
@@ -201,7 +265,7 @@ conv3d_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
                     tmem_ld16(acc + (uint32_t)c, v);
                     tmem_ld_wait();
                     const int ch0 = t.n0 + c;
-                    if (!row_ok || ch0 >= p.Cout) continue;
+                    if (ch0 >= p.Cout) continue;              // warp-uniform
                     float f[16];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
@@ -211,19 +275,22 @@ conv3d_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
                             if (ch0 + j < p.Cout) f[j] += __ldg(p.bias + ch0 + j);
                     }
                     if (p.out_planar) {
+                        if (row_ok) {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            if (ch0 + j >= p.Cout) break;
-                            const long long idx = ((long long)t.nb * p.Cout + ch0 + j) * DHW + vox;
-                            float val = f[j];
-                            if (first_split && p.residual) val += p.residual[idx];
-                            if (p.atomic_out) atomicAdd(p.out + idx, val);
-                            else p.out[idx] = val;
+                            for (int j = 0; j < 16; ++j) {
+                                if (ch0 + j >= p.Cout) break;
+                                const long long idx = ((long long)t.nb * p.Cout + ch0 + j) * DHW + vox;
+                                float val = f[j];
+                                if (first_split && p.residual) val += p.residual[idx];
+                                if (p.atomic_out) atomicAdd(p.out + idx, val);
+                                else p.out[idx] = val;
+                            }
                         }
                     } else {
                         const long long base = ((long long)t.nb * DHW + vox) * p.out_ld + p.out_c0 + ch0;
-                        if (ch0 + 16 <= p.Cout && ((base & 3) == 0)) {
-                            if (first_split && p.residual) {
+                        const bool vec = (ch0 + 16 <= p.Cout) && ((base & 3) == 0);
+                        if (row_ok && first_split && p.residual) {
+                            if (vec) {
                                 const float4* rp = reinterpret_cast<const float4*>(p.residual + base);
 #pragma unroll
                                 for (int j = 0; j < 4; ++j) {
@@ -231,26 +298,49 @@ conv3d_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
                                     f[4 * j + 0] += rv.x; f[4 * j + 1] += rv.y;
                                     f[4 * j + 2] += rv.z; f[4 * j + 3] += rv.w;
                                 }
-                            }
-                            if (p.atomic_out) {
-#pragma unroll
-                                for (int j = 0; j < 4; ++j)
-                                    red_add_v4(p.out + base + 4 * j, f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
                             } else {
-                                float4* op = reinterpret_cast<float4*>(p.out + base);
 #pragma unroll
-                                for (int j = 0; j < 4; ++j)
-                                    op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                                for (int j = 0; j < 16; ++j)
+                                    if (ch0 + j < p.Cout) f[j] += p.residual[base + j];
                             }
-                        } else {
+                        }
+                        if (row_ok) {
+                            if (vec) {
+                                if (p.atomic_out) {
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j)
+                                        red_add_v4(p.out + base + 4 * j, f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                                } else {
+                                    float4* op = reinterpret_cast<float4*>(p.out + base);
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j)
+                                        op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                                }
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) {
+                                    if (ch0 + j >= p.Cout) break;
+                                    if (p.atomic_out) atomicAdd(p.out + base + j, f[j]);
+                                    else p.out[base + j] = f[j];
+                                }
+                            }
+                        }
+                        if (do_stats) {
+                            // f[] now holds the final output values of this voxel row: column sums over the warp
+                            float sq[16];
 #pragma unroll
                             for (int j = 0; j < 16; ++j) {
-                                if (ch0 + j >= p.Cout) break;
-                                float val = f[j];
-                                if (first_split && p.residual) val += p.residual[base + j];
-                                if (p.atomic_out) atomicAdd(p.out + base + j, val);
-                                else p.out[base + j] = val;
+                                if (!row_ok || ch0 + j >= p.Cout) f[j] = 0.f;
+                                sq[j] = f[j] * f[j];
                             }
+                            const float s1 = warp_colsum16(f, lane);
+                            const float s2 = warp_colsum16(sq, lane);
+                            const int chn = ch0 + stats_channel_of_lane(lane);
+                            if ((lane & 1) == 0 && chn < p.Cout) {
+                                my_stats[chn] += s1;
+                                my_stats[kStatsMaxC + chn] += s2;
+                            }
+                            __syncwarp();
                         }
                     }
                 }
@@ -260,6 +350,7 @@ conv3d_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
             if (lane == 0) mbar_arrive(&ctl->tempty[as]);
             if (++as == p.acc_sets) { as = 0; aph ^= 1; }
         }
+        if (do_stats && stats_nb >= 0 && ok) flush_stats(stats_nb);
     }
 
     tc_fence_before();
@@ -490,7 +581,17 @@ int conv_plan_create(const ConvDesc& d, int* d_err_flag, ConvPlan& plan, char* e
     if (p.w_stages * p.w_stage_bytes + 2 * p.s_stage_bytes > avail) return fail("tile does not fit in shared memory");
     p.s_stages = std::min(kMaxSStages, (avail - p.w_stages * p.w_stage_bytes) / p.s_stage_bytes);
     p.s_stages = std::min(p.s_stages, 6);
-    plan.smem_bytes = p.w_stages * p.w_stage_bytes + p.s_stages * p.s_stage_bytes + 2048;
+    plan.fused_stats = d.stats != nullptr && split == 1 && d.Cout <= kStatsMaxC && !d.out_planar;
+    const int ctl_bytes = 2048 + (plan.fused_stats ? kStatsSmemBytes : 0);
+    {
+        const int avail2 = 227 * 1024 - ctl_bytes;
+        while (p.s_stages > 2 && p.w_stages * p.w_stage_bytes + p.s_stages * p.s_stage_bytes > avail2) --p.s_stages;
+        if (p.w_stages * p.w_stage_bytes + p.s_stages * p.s_stage_bytes > avail2) {
+            if (p.w_stages == 2) p.w_stages = 1;
+        }
+        if (p.w_stages * p.w_stage_bytes + p.s_stages * p.s_stage_bytes > avail2) return fail("no room for the statistics scratch");
+    }
+    plan.smem_bytes = p.w_stages * p.w_stage_bytes + p.s_stages * p.s_stage_bytes + ctl_bytes;
 
     if (encode_a_maps(d, p, enc, err, errlen)) return 1;
     {
@@ -512,6 +613,7 @@ int conv_plan_create(const ConvDesc& d, int* d_err_flag, ConvPlan& plan, char* e
     p.bias = d.bias; p.residual = d.residual; p.out = d.out;
     p.out_ld = d.out_ld ? d.out_ld : d.Cout; p.out_c0 = d.out_c0; p.out_planar = d.out_planar;
     p.err_flag = d_err_flag;
+    p.stats = plan.fused_stats ? d.stats : nullptr;
     p.desc_xor = 0;
     plan.out_bytes = d.out_planar ? (size_t)d.NB * d.Cout * d.D * d.H * d.W * 4
                                   : (size_t)d.NB * d.D * d.H * d.W * p.out_ld * 4;

@@ -72,6 +72,8 @@ struct ConvKernelParams {
     int out_c0;              // channel offset inside the row
     int out_planar;          // 1: write NCDHW (out[(n*Cout+c)*DHW + vox])
     int atomic_out;          // 1: red.add into out (split_k > 1); out must be pre-zeroed
+    double* stats;           // optional [NB][Cout][2] = (sum, sum of squares) of the outputs over voxels,
+                             // accumulated by the epilogue (fused LayerNorm/GroupNorm statistics); or nullptr
     int* err_flag;           // device int, set non-zero on pipeline timeout
     uint64_t desc_xor;       // bring-up only: xor into every smem matrix descriptor (0 in product use)
 };
@@ -100,6 +102,7 @@ struct ConvDesc {
     const float* residual = nullptr;
     float* out = nullptr;
     int out_ld = 0, out_c0 = 0, out_planar = 0;
+    double* stats = nullptr;           // request fused output statistics (honoured iff plan.fused_stats)
     int split_k = 1;                   // >1 => atomics into pre-zeroed out
     int block_n = 0;                   // 0 = choose
     int td = 0;                        // 0 = choose
@@ -123,6 +126,7 @@ struct ConvPlan {
     int grid = 0;
     int smem_bytes = 0;
     bool needs_zero = false;   // out must be zeroed before launch (atomic_out)
+    bool fused_stats = false;  // the epilogue accumulates ConvDesc::stats (needs split_k == 1, Cout <= 256)
     size_t out_bytes = 0;
 };
 

@@ -127,6 +127,11 @@ int main(int argc, char** argv) {
         CK(cudaMemset(d_out, 0xFF, out_elems * 4));   // NaN pattern: unwritten outputs are caught
         d.out = d_out; d.out_ld = c.Cout;
 
+        double* d_stats = nullptr;
+        CK(cudaMalloc(&d_stats, (size_t)c.NB * c.Cout * 2 * sizeof(double)));
+        CK(cudaMemset(d_stats, 0, (size_t)c.NB * c.Cout * 2 * sizeof(double)));
+        d.stats = d_stats;
+
         CK(cudaMemset(d_err, 0, sizeof(int)));
         ConvPlan plan;
         char err[256] = {0};
@@ -212,7 +217,25 @@ int main(int argc, char** argv) {
                 if (e > 2e-3 * std::max(1.0, std::fabs(acc))) ++bad;
             }
         }
-        const bool pass = (bad == 0 && nan_cnt == 0);
+        // fused statistics: per-(sample, channel) sum and sum of squares of the outputs
+        size_t stats_bad = 0;
+        if (plan.fused_stats && !c.timing) {
+            std::vector<double> h_stats((size_t)c.NB * c.Cout * 2);
+            CK(cudaMemcpy(h_stats.data(), d_stats, h_stats.size() * sizeof(double), cudaMemcpyDeviceToHost));
+            const size_t vpb = (size_t)Do * Do * Do;
+            for (int nb = 0; nb < c.NB; ++nb)
+                for (int co = 0; co < c.Cout; ++co) {
+                    double s = 0, q = 0;
+                    for (size_t v = 0; v < vpb; ++v) { const double x = h_out[((size_t)nb * vpb + v) * c.Cout + co]; s += x; q += x * x; }
+                    const double gs = h_stats[((size_t)nb * c.Cout + co) * 2], gq = h_stats[((size_t)nb * c.Cout + co) * 2 + 1];
+                    if (std::fabs(gs - s) > 1e-3 * (1 + std::fabs(s)) + 1e-4 * std::sqrt(q * vpb) || std::fabs(gq - q) > 1e-4 * (1 + q)) {
+                        if (stats_bad < 3) printf("   stats mismatch nb=%d co=%d: sum %g vs %g, sumsq %g vs %g\n", nb, co, gs, s, gq, q);
+                        ++stats_bad;
+                    }
+                }
+            printf("[%s] fused stats checked: bad=%zu\n", c.name.c_str(), stats_bad);
+        }
+        const bool pass = (bad == 0 && nan_cnt == 0 && stats_bad == 0);
         printf("[%s] %s max_err=%.3e max_ref=%.3f bad=%zu nan=%zu\n", c.name.c_str(), pass ? "PASS" : "FAIL", max_err, max_ref, bad, nan_cnt);
         if (!pass) {
             ++n_fail;
@@ -223,7 +246,7 @@ int main(int argc, char** argv) {
 
         conv_plan_destroy(plan);
         for (auto p : d_src) cudaFree(p);
-        cudaFree(d_w); cudaFree(d_bias); cudaFree(d_res); cudaFree(d_out);
+        cudaFree(d_w); cudaFree(d_bias); cudaFree(d_res); cudaFree(d_out); cudaFree(d_stats);
     }
     printf("SUMMARY run=%d fail=%d\n", n_run, n_fail);
     return n_fail ? 1 : 0;

@@ -16,6 +16,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <map>
@@ -35,6 +36,7 @@ struct HostTensor {
 struct DevT {          // fp32 activation [NB][sp^3][C]
     float* p = nullptr;
     int C = 0, sp = 0;
+    double* stats = nullptr;   // [NB][C][2] (sum, sumsq over voxels), filled by the producer when requested
 };
 
 struct ConvOp {
@@ -69,8 +71,15 @@ struct UNet {
     __half* feat_staging = nullptr;    // for forward_ncdhw / forward_host
     float* out_staging = nullptr;
     std::string error;
+    // whole-forward CUDA graph, keyed by (batch, input pointer, output pointer)
+    cudaGraphExec_t gexec = nullptr;
+    const void* g_feat = nullptr;
+    float* g_out = nullptr;
+    int g_nb = 0;
+    bool use_graph = true;
 
     ~UNet() {
+        if (gexec) cudaGraphExecDestroy(gexec);
         for (auto& c : convs) conv_plan_destroy(c->plan);
         for (void* p : allocs) cudaFree(p);
     }
@@ -153,8 +162,10 @@ struct Builder {
     struct ConvIn { F16 t; int ks; int cin_real; std::string wname; };
 
     // out[C_out] = sum_i conv_ks_i(in_i) + sum of biases (+ residual)
+    // want_stats: the output feeds a LayerNorm / GroupNorm -> per-(n,c) moments are produced too, by the conv
+    // epilogue when possible (no split-K), else by a moments launch right after the conv.
     ConvOp* emit_conv(const std::vector<ConvIn>& ins, int sp_out, int stride, int Cout, const float* residual,
-                      float* out, bool planar, const std::vector<std::string>& bias_names) {
+                      float* out, bool planar, const std::vector<std::string>& bias_names, DevT* want_stats = nullptr) {
         auto op = std::make_unique<ConvOp>();
         const double flops_before = u.flops;
         ConvDesc& d = op->desc;
@@ -201,6 +212,7 @@ struct Builder {
         d.bias = upload(bias);
         d.residual = residual;
         d.out = out; d.out_ld = Cout; d.out_c0 = 0; d.out_planar = planar ? 1 : 0;
+        if (want_stats) { want_stats->stats = stats_slot(Cout); d.stats = want_stats->stats; }
         char e[256] = {0};
         if (conv_plan_create(d, u.d_err, op->plan, e, sizeof(e))) { fail(e); return nullptr; }
         ConvOp* raw = op.get();
@@ -214,7 +226,9 @@ struct Builder {
             return conv_plan_launch(pl, st);
         });
         u.op_kinds.push_back(PIXIE_OP_CONV); u.op_flops.push_back(u.flops - flops_before);
+        const bool fused = raw->plan.fused_stats;
         u.convs.push_back(std::move(op));
+        if (want_stats && !fused) emit_moments(*want_stats, want_stats->stats);
         return raw;
     }
 
@@ -244,18 +258,15 @@ struct Builder {
         if (has_skip) raw = alloc_f16(Cin, sp);
         int c0 = 0;
         for (auto& x : xs) {
-            double* st = stats_slot(x.C);
-            emit_moments(x, st);
-            emit_norm(x, st, kNormLN, 1, dg1, db1, kActLeaky, &a, c0, has_skip ? &raw : nullptr, c0);
+            if (!x.stats) { fail("internal: input of " + path + " has no statistics"); return {}; }
+            emit_norm(x, x.stats, kNormLN, 1, dg1, db1, kActLeaky, &a, c0, has_skip ? &raw : nullptr, c0);
             c0 += x.C;
         }
         DevT t = alloc_f32(Cout, sp, "");
         if (!emit_conv({{a, 3, Cin, path + ".in_layers.2.weight"}}, sp, 1, Cout, nullptr, t.p, false,
-                       {path + ".in_layers.2.bias"})) return {};
+                       {path + ".in_layers.2.bias"}, &t)) return {};
         F16 b = alloc_f16(Cout, sp);
-        double* st2 = stats_slot(Cout);
-        emit_moments(t, st2);
-        emit_norm(t, st2, kNormLN, 1, dg2, db2, kActLeaky, &b, 0, nullptr, 0);
+        emit_norm(t, t.stats, kNormLN, 1, dg2, db2, kActLeaky, &b, 0, nullptr, 0);
         DevT out = alloc_f32(Cout, sp, path);
         std::vector<ConvIn> ins = {{b, 3, Cout, path + ".out_layers.3.weight"}};
         std::vector<std::string> biases = {path + ".out_layers.3.bias"};
@@ -263,7 +274,8 @@ struct Builder {
             ins.push_back({raw, 1, Cin, path + ".skip_connection.weight"});
             biases.push_back(path + ".skip_connection.bias");
         }
-        if (!emit_conv(ins, sp, 1, Cout, has_skip ? nullptr : xs[0].p, out.p, false, biases)) return {};
+        if (!emit_conv(ins, sp, 1, Cout, has_skip ? nullptr : xs[0].p, out.p, false, biases, &out)) return {};
+        u.named[path] = out;
         return out;
     }
 
@@ -272,7 +284,7 @@ struct Builder {
         emit_norm(x, nullptr, kNormNone, 1, nullptr, nullptr, kActNone, nullptr, 0, &raw, 0);
         const int sp_out = (x.sp + 1) / 2;
         DevT out = alloc_f32(x.C, sp_out, path);
-        if (!emit_conv({{raw, 3, x.C, path + ".op.weight"}}, sp_out, 2, x.C, nullptr, out.p, false, {path + ".op.bias"})) return {};
+        if (!emit_conv({{raw, 3, x.C, path + ".op.weight"}}, sp_out, 2, x.C, nullptr, out.p, false, {path + ".op.bias"}, &out)) return {};
         return out;
     }
 
@@ -285,7 +297,7 @@ struct Builder {
             u.op_kinds.push_back(PIXIE_OP_UPSAMPLE); u.op_flops.push_back(0);
         }
         DevT out = alloc_f32(x.C, 2 * x.sp, path);
-        if (!emit_conv({{up, 3, x.C, path + ".conv.weight"}}, 2 * x.sp, 1, x.C, nullptr, out.p, false, {path + ".conv.bias"})) return {};
+        if (!emit_conv({{up, 3, x.C, path + ".conv.weight"}}, 2 * x.sp, 1, x.C, nullptr, out.p, false, {path + ".conv.bias"}, &out)) return {};
         return out;
     }
 
@@ -295,9 +307,8 @@ struct Builder {
         const HostTensor* b = param(path + ".norm.bias", (size_t)C);
         if (!g || !b) return {};
         F16 n = alloc_f16(C, x.sp);
-        double* st = stats_slot(C);
-        emit_moments(x, st);
-        emit_norm(x, st, kNormGN, 32, upload(g->data), upload(b->data), kActNone, &n, 0, nullptr, 0);
+        if (!x.stats) { fail("internal: attention input has no statistics"); return {}; }
+        emit_norm(x, x.stats, kNormGN, 32, upload(g->data), upload(b->data), kActNone, &n, 0, nullptr, 0);
         DevT qkv = alloc_f32(3 * C, x.sp, "");
         if (!emit_conv({{n, 1, C, path + ".qkv.weight"}}, x.sp, 1, 3 * C, nullptr, qkv.p, false, {path + ".qkv.bias"})) return {};
         F16 at = alloc_f16(C, x.sp);
@@ -308,7 +319,7 @@ struct Builder {
             u.op_kinds.push_back(PIXIE_OP_ATTENTION); u.op_flops.push_back(0);
         }
         DevT out = alloc_f32(C, x.sp, path);
-        if (!emit_conv({{at, 1, C, path + ".proj_out.weight"}}, x.sp, 1, C, x.p, out.p, false, {path + ".proj_out.bias"})) return {};
+        if (!emit_conv({{at, 1, C, path + ".proj_out.weight"}}, x.sp, 1, C, x.p, out.p, false, {path + ".proj_out.bias"}, &out)) return {};
         return out;
     }
 
@@ -334,47 +345,39 @@ struct Builder {
         } else if (c.feature_channels > c.cond_dim) {
             const int Hc = 128;
             DevT c0 = alloc_f32(Hc, G, "projector.net.0");
-            if (!emit_conv({{feat, 1, c.feature_channels, "projector.net.0.weight"}}, G, 1, Hc, nullptr, c0.p, false, {"projector.net.0.bias"})) return false;
+            if (!emit_conv({{feat, 1, c.feature_channels, "projector.net.0.weight"}}, G, 1, Hc, nullptr, c0.p, false, {"projector.net.0.bias"}, &c0)) return false;
             const HostTensor *g1 = param("projector.net.1.weight", Hc), *b1 = param("projector.net.1.bias", Hc);
             if (!g1 || !b1) return false;
             F16 a1 = alloc_f16(Hc, G);
-            double* s1 = stats_slot(Hc);
-            emit_moments(c0, s1);
-            emit_norm(c0, s1, kNormGN, 32, upload(g1->data), upload(b1->data), kActSiLU, &a1, 0, nullptr, 0);
+            emit_norm(c0, c0.stats, kNormGN, 32, upload(g1->data), upload(b1->data), kActSiLU, &a1, 0, nullptr, 0);
             DevT c1 = alloc_f32(Hc, G, "projector.net.3");
-            if (!emit_conv({{a1, 3, Hc, "projector.net.3.weight"}}, G, 1, Hc, nullptr, c1.p, false, {"projector.net.3.bias"})) return false;
+            if (!emit_conv({{a1, 3, Hc, "projector.net.3.weight"}}, G, 1, Hc, nullptr, c1.p, false, {"projector.net.3.bias"}, &c1)) return false;
             const HostTensor *g2 = param("projector.net.4.weight", Hc), *b2 = param("projector.net.4.bias", Hc);
             if (!g2 || !b2) return false;
             F16 a2 = alloc_f16(Hc, G);
-            double* s2 = stats_slot(Hc);
-            emit_moments(c1, s2);
-            emit_norm(c1, s2, kNormGN, 32, upload(g2->data), upload(b2->data), kActSiLU, &a2, 0, nullptr, 0);
+            emit_norm(c1, c1.stats, kNormGN, 32, upload(g2->data), upload(b2->data), kActSiLU, &a2, 0, nullptr, 0);
             DevT c2 = alloc_f32(c.cond_dim, G, "projector.net.6");
-            if (!emit_conv({{a2, 1, Hc, "projector.net.6.weight"}}, G, 1, c.cond_dim, nullptr, c2.p, false, {"projector.net.6.bias"})) return false;
+            if (!emit_conv({{a2, 1, Hc, "projector.net.6.weight"}}, G, 1, c.cond_dim, nullptr, c2.p, false, {"projector.net.6.bias"}, &c2)) return false;
             const HostTensor *g3 = param("projector.net.7.weight", c.cond_dim), *b3 = param("projector.net.7.bias", c.cond_dim);
             if (!g3 || !b3) return false;
             unet_in = alloc_f16((c.cond_dim + 63) / 64 * 64, G);     // zero-padded channels stay zero
-            double* s3 = stats_slot(c.cond_dim);
-            emit_moments(c2, s3);
-            emit_norm(c2, s3, kNormGN, 32, upload(g3->data), upload(b3->data), kActNone, &unet_in, 0, nullptr, 0);
+            emit_norm(c2, c2.stats, kNormGN, 32, upload(g3->data), upload(b3->data), kActNone, &unet_in, 0, nullptr, 0);
         } else {
             // light projector: Conv3d 1x1 -> GroupNorm(max(out/2,1)) -> SiLU
             DevT c0 = alloc_f32(c.cond_dim, G, "projector.net.0");
-            if (!emit_conv({{feat, 1, c.feature_channels, "projector.net.0.weight"}}, G, 1, c.cond_dim, nullptr, c0.p, false, {"projector.net.0.bias"})) return false;
+            if (!emit_conv({{feat, 1, c.feature_channels, "projector.net.0.weight"}}, G, 1, c.cond_dim, nullptr, c0.p, false, {"projector.net.0.bias"}, &c0)) return false;
             const HostTensor *g1 = param("projector.net.1.weight", c.cond_dim), *b1 = param("projector.net.1.bias", c.cond_dim);
             if (!g1 || !b1) return false;
             unet_in = alloc_f16((c.cond_dim + 63) / 64 * 64, G);
-            double* s1 = stats_slot(c.cond_dim);
-            emit_moments(c0, s1);
             const int groups = c.cond_dim / 2 > 1 ? c.cond_dim / 2 : 1;
-            emit_norm(c0, s1, kNormGN, groups, upload(g1->data), upload(b1->data), kActSiLU, &unet_in, 0, nullptr, 0);
+            emit_norm(c0, c0.stats, kNormGN, groups, upload(g1->data), upload(b1->data), kActSiLU, &unet_in, 0, nullptr, 0);
         }
 
         // ---- MyUNetModel (:734-873); same construction order so module paths match the state dict
         const int mc = c.model_channels;
         std::vector<DevT> hs;
         DevT h = alloc_f32(mc, G, "unet.input_blocks.0");
-        if (!emit_conv({{unet_in, 3, c.cond_dim, "unet.input_blocks.0.0.weight"}}, G, 1, mc, nullptr, h.p, false, {"unet.input_blocks.0.0.bias"})) return false;
+        if (!emit_conv({{unet_in, 3, c.cond_dim, "unet.input_blocks.0.0.weight"}}, G, 1, mc, nullptr, h.p, false, {"unet.input_blocks.0.0.bias"}, &h)) return false;
         u.first_conv = u.convs[first_conv_idx].get();
         hs.push_back(h);
         int ch = mc, sp = G, blk = 1;
@@ -423,9 +426,8 @@ struct Builder {
             const HostTensor *g = param("unet.out.0.weight", V), *b = param("unet.out.0.bias", V);
             if (!g || !b) return false;
             F16 a = alloc_f16(mc, G);
-            double* st = stats_slot(mc);
-            emit_moments(h, st);
-            emit_norm(h, st, kNormLN, 1, upload(g->data), upload(b->data), kActLeaky, &a, 0, nullptr, 0);
+            if (!h.stats) return fail("internal: head input has no statistics");
+            emit_norm(h, h.stats, kNormLN, 1, upload(g->data), upload(b->data), kActLeaky, &a, 0, nullptr, 0);
             u.out_staging = dalloc<float>((size_t)NB * c.out_channels * V);
             u.head_conv = emit_conv({{a, 3, mc, "unet.out.2.weight"}}, G, 1, c.out_channels, nullptr, u.out_staging, true, {"unet.out.2.bias"});
             if (!u.head_conv) return false;
@@ -446,6 +448,7 @@ UNet* unet_create(const pixie_unet_config& cfg, std::string& err) {
     if (cfg.precision != 0 && cfg.precision != 1) { err = "precision must be 0 or 1"; return nullptr; }
     auto* u = new UNet();
     u->cfg = cfg;
+    u->use_graph = getenv("PIXIE_NO_GRAPH") == nullptr;
     u->NBmax = cfg.max_batch > 0 ? cfg.max_batch : 1;
     return u;
 }
@@ -470,14 +473,40 @@ int unet_finalize(UNet* u) {
     return 0;
 }
 
-static int run_ops(UNet* u, int batch, cudaStream_t st) {
-    u->cur_nb = batch;
+static int enqueue_ops(UNet* u, cudaStream_t st) {
     cudaMemsetAsync(u->d_stats, 0, u->stats_doubles * sizeof(double), st);
     for (auto& op : u->ops) {
         const int rc = op(st);
         if (rc) { u->error = "kernel launch failed, cuda error " + std::to_string(rc); return 1; }
     }
     return 0;
+}
+
+static int run_ops(UNet* u, int batch, const void* feat, float* out, cudaStream_t st) {
+    u->cur_nb = batch;
+    if (u->use_graph) {
+        if (!(u->gexec && u->g_nb == batch && u->g_feat == feat && u->g_out == out)) {
+            if (u->gexec) { cudaGraphExecDestroy(u->gexec); u->gexec = nullptr; }
+            cudaStream_t cs;                      // the caller's stream may be the legacy default stream, which cannot capture
+            cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking);
+            cudaGraph_t g = nullptr;
+            bool ok = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+            if (ok) {
+                const int rc = enqueue_ops(u, cs);
+                ok = (cudaStreamEndCapture(cs, &g) == cudaSuccess) && g && rc == 0;
+            }
+            if (ok) ok = cudaGraphInstantiate(&u->gexec, g, 0) == cudaSuccess;
+            if (g) cudaGraphDestroy(g);
+            cudaStreamDestroy(cs);
+            if (!ok) { cudaGetLastError(); u->gexec = nullptr; u->use_graph = false; }
+            u->g_nb = batch; u->g_feat = feat; u->g_out = out;
+        }
+        if (u->gexec) {
+            if (cudaGraphLaunch(u->gexec, st) != cudaSuccess) { u->error = "cudaGraphLaunch failed"; return 1; }
+            return 0;
+        }
+    }
+    return enqueue_ops(u, st);
 }
 
 static int check_err_flag(UNet* u) {
@@ -499,7 +528,7 @@ int unet_forward(UNet* u, const void* feat_f16, int batch, float* out, cudaStrea
         if (conv_plan_retarget(fc->desc, fc->plan, e, sizeof(e))) { u->error = e; return 1; }
     }
     u->head_conv->plan.p.out = out;
-    return run_ops(u, batch, st);
+    return run_ops(u, batch, feat_f16, out, st);
 }
 
 int unet_profile(UNet* u, const void* feat_f16, int batch, float* out, cudaStream_t st, float* ms, int* kinds, double* flops, int cap) {

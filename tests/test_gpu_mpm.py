@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
-def _pair(n, ng, materials, seed, prec="f32", bcs=True, g=(0.0, 0.0, -9.8), damping=0.9999):
+def _pair(n, ng, materials, seed, prec="f32", bcs=True, g=(0.0, 0.0, -9.8), damping=0.9999, moving=True):
     from pixie_b200.mpm_solver_warp import MPM_Simulator_WARP
     sc = R.synthetic_scene(n, ng, seed=seed, materials=materials)
     s = MPM_Simulator_WARP(10)
@@ -36,10 +36,13 @@ def _pair(n, ng, materials, seed, prec="f32", bcs=True, g=(0.0, 0.0, -9.8), damp
                  softening=0.1, plastic_viscosity=10.0)
     if bcs:
         s.add_bounding_box(); o.add_bc(R.BC_BBOX)
-        s.set_velocity_on_cuboid(point=[1.0, 1.0, 0.62], size=[0.5, 0.5, 0.04], velocity=[0, 0, 0])
-        o.add_bc(R.BC_CUBOID, point=[1.0, 1.0, 0.62], size=[0.5, 0.5, 0.04])
-        s.set_velocity_on_cuboid(point=[0.7, 1.0, 1.3], size=[0.05, 0.2, 0.05], velocity=[0.5, 0, 0], start_time=0.0, end_time=0.01, reset=1)
-        o.add_bc(R.BC_CUBOID, point=[0.7, 1.0, 1.3], size=[0.05, 0.2, 0.05], velocity=[0.5, 0, 0], end_time=0.01, reset=1)
+        # box faces deliberately off the grid nodes: a face that coincides with a node makes the fp32
+        # inside/outside test (|i*dx - c| < size) a coin flip against any other precision
+        s.set_velocity_on_cuboid(point=[1.0, 1.0, 0.62], size=[0.51, 0.51, 0.04], velocity=[0, 0, 0])
+        o.add_bc(R.BC_CUBOID, point=[1.0, 1.0, 0.62], size=[0.51, 0.51, 0.04])
+        if moving:
+            s.set_velocity_on_cuboid(point=[0.7, 1.0, 1.3], size=[0.05, 0.2, 0.05], velocity=[0.5, 0, 0], start_time=0.0, end_time=0.01, reset=1)
+            o.add_bc(R.BC_CUBOID, point=[0.7, 1.0, 1.3], size=[0.05, 0.2, 0.05], velocity=[0.5, 0, 0], end_time=0.01, reset=1)
         s.add_surface_collider(point=[1.0, 1.0, 0.1], normal=[0, 0, 2], surface="sticky", friction=0.0, start_time=0.0, end_time=1e3)
         o.add_bc(R.BC_SURFACE, point=[1.0, 1.0, 0.1], normal=[0, 0, 1], end_time=1e3)
         p, sz = np.float32([1.0, 1.0, 1.2]), np.float32([0.2, 0.2, 0.1])
@@ -136,8 +139,9 @@ def test_conservation_at_full_size(built_lib, cuda_dev):
 
 def test_drift_vs_fp64_oracle(built_lib, cuda_dev):
     """Position drift against the fp64 oracle over a rollout, next to the fp32-oracle noise floor."""
-    s, o64, _ = _pair(20_000, 48, (0,), seed=1, prec="f64")
-    _, o32, _ = _pair(20_000, 48, (0,), seed=1, prec="f32")
+    # (no moving collider here: the step at which its faces cross a node is precision dependent by design)
+    s, o64, _ = _pair(20_000, 48, (0,), seed=1, prec="f64", moving=False)
+    _, o32, _ = _pair(20_000, 48, (0,), seed=1, prec="f32", moving=False)
     s.p2g2p_n(300, 1e-4); o64.step(300, 1e-4); o32.step(300, 1e-4)
     torch.cuda.synchronize()
     drift = _err(s, o64, "X")
