@@ -188,6 +188,11 @@ int pixie_mpm_apply_additional_params(pixie_mpm_t h, const float* boxes_host, in
 int pixie_mpm_select_box(pixie_mpm_t h, const float point[3], const float size[3], int* mask_dev, void* stream);
 int pixie_mpm_select_cylinder(pixie_mpm_t h, const float point[3], const float normal[3],
                               float half_height, float radius, int* mask_dev, void* stream);
+/* The solver keeps a cell-sorted private copy of the particle state between steps. pixie_mpm_sync writes
+ * results back into the bound arrays (no-op if they are current) and must precede any read of them; every
+ * other entry point that touches the bound arrays calls it internally. After a sync the caller may modify
+ * its arrays: the next step re-reads them. */
+int pixie_mpm_sync(pixie_mpm_t h, void* stream);
 /* Borrowed pointers to the grid arrays owned by the handle: grid_m [n^3], grid_v_in / grid_v_out
  * [n^3][3] as left by the last substep (for tests). */
 int pixie_mpm_grid_ptrs(pixie_mpm_t h, float** grid_mv4, float** grid_v_out);

@@ -130,6 +130,7 @@ int pixie_mpm_select_box(pixie_mpm_t h, const float point[3], const float size[3
 int pixie_mpm_select_cylinder(pixie_mpm_t h, const float point[3], const float normal[3], float hh, float radius, int* mask, void* s) {
     MPM_CALL(pixie::mpm_select_cylinder(h->m, point, normal, hh, radius, mask, (cudaStream_t)s));
 }
+int pixie_mpm_sync(pixie_mpm_t h, void* s) { MPM_CALL(pixie::mpm_sync(h->m, (cudaStream_t)s)); }
 int pixie_mpm_grid_ptrs(pixie_mpm_t h, float** mv4, float** v4) { MPM_CALL(pixie::mpm_grid_ptrs(h->m, mv4, v4)); }
 int pixie_mpm_launches_per_substep(pixie_mpm_t h) { (void)h; return 3; }
 void pixie_mpm_destroy(pixie_mpm_t h) {

@@ -182,26 +182,44 @@ conv3d_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
                     if (!ok) break;
                     tc_fence_after();
                     const uint32_t s16 = (s_base0 + (uint32_t)(ss * p.s_stage_bytes)) >> 4;
-                    for (int kd = 0; kd < n_kd; ++kd) {
-                        const int d = pl - kd;
-                        if (d < 0 || d >= t.tde) continue;
-                        const uint32_t acc = tmem_base + (uint32_t)((as * p.TD + d) * p.block_n);
-                        uint32_t first = ((touched >> d) & 1u) ^ 1u;          // 1: this accumulator is still empty
-                        touched |= (1u << d);
-                        for (int kh = 0; kh < n_kh; ++kh) {
-                            const uint64_t da = desc_fixed | (uint64_t)((s16 + (uint32_t)kh * kh_stride16) & 0x3FFFu);
-                            const uint64_t db = desc_fixed | (uint64_t)((w16 + (uint32_t)(kd * n_kh + kh) * tap_stride16) & 0x3FFFu);
-                            if (elect_one()) {
-                                // 4 x (128 x N x 16) MMAs: K advances by 32 B = 2 descriptor units inside the swizzle atom
-                                umma_f16(acc, da, db, idesc, first ^ 1u);
+                    // taps served by this slab: kd in [kd_lo, kd_hi] (accumulator d = pl - kd must exist)
+                    const int kd_lo = max(0, pl - (t.tde - 1)), kd_hi = min(n_kd - 1, pl);
+                    if (elect_one()) {
+                        if (n_kh == 3) {
+                            for (int kd = kd_lo; kd <= kd_hi; ++kd) {
+                                const int d = pl - kd;
+                                const uint32_t acc = tmem_base + (uint32_t)((as * p.TD + d) * p.block_n);
+                                const uint32_t fresh = ((touched >> d) & 1u) ^ 1u;    // 1: accumulator d still empty
+                                touched |= (1u << d);
+                                const uint64_t da0 = desc_fixed | (uint64_t)(s16 & 0x3FFFu);
+                                const uint64_t db0 = desc_fixed | (uint64_t)((w16 + (uint32_t)(kd * 3) * tap_stride16) & 0x3FFFu);
+#pragma unroll
+                                for (int kh = 0; kh < 3; ++kh) {
+                                    const uint64_t da = da0 + (uint64_t)(kh * kh_stride16);
+                                    const uint64_t db = db0 + (uint64_t)(kh * tap_stride16);
+                                    umma_f16(acc, da, db, idesc, (kh == 0) ? (fresh ^ 1u) : 1u);
+                                    umma_f16(acc, da + 2, db + 2, idesc, 1u);
+                                    umma_f16(acc, da + 4, db + 4, idesc, 1u);
+                                    umma_f16(acc, da + 6, db + 6, idesc, 1u);
+                                }
+                            }
+                        } else {
+                            for (int kd = kd_lo; kd <= kd_hi; ++kd) {
+                                const int d = pl - kd;
+                                const uint32_t acc = tmem_base + (uint32_t)((as * p.TD + d) * p.block_n);
+                                const uint32_t fresh = ((touched >> d) & 1u) ^ 1u;
+                                touched |= (1u << d);
+                                const uint64_t da = desc_fixed | (uint64_t)(s16 & 0x3FFFu);
+                                const uint64_t db = desc_fixed | (uint64_t)((w16 + (uint32_t)kd * tap_stride16) & 0x3FFFu);
+                                umma_f16(acc, da, db, idesc, fresh ^ 1u);
                                 umma_f16(acc, da + 2, db + 2, idesc, 1u);
                                 umma_f16(acc, da + 4, db + 4, idesc, 1u);
                                 umma_f16(acc, da + 6, db + 6, idesc, 1u);
                             }
-                            first = 0;
                         }
+                        umma_commit(&ctl->sempty[ss]);        // slab slot free once these MMAs retire
                     }
-                    if (elect_one()) umma_commit(&ctl->sempty[ss]);   // slab slot free once these MMAs retire
+                    for (int kd = kd_lo; kd <= kd_hi; ++kd) touched |= (1u << (pl - kd));   // keep the mask warp-uniform
                     if (++ss == p.s_stages) { ss = 0; sph ^= 1; }
                 }
                 if (elect_one()) umma_commit(&ctl->wempty[ws]);
@@ -551,6 +569,20 @@ int conv_plan_create(const ConvDesc& d, int* d_err_flag, ConvPlan& plan, char* e
     int td = d.td ? d.td : std::min(4, 512 / (2 * bn));
     td = std::max(1, std::min(td, d.D));
     if (!any3) td = std::min(td, 2);    // no plane re-use without kd taps: smaller tiles, more CTAs
+    if (!d.td && td > 1) {
+        // wave quantisation: a persistent grid of `sms` CTAs finishes in ceil(tiles/sms) rounds; prefer the
+        // plane count with the better last-round fill (64^3: TD=4 -> 512 tiles = 3.46 rounds, TD=2 -> 6.92)
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        auto fill = [&](int t) {
+            const long long tiles = (long long)d.NB * ((d.W + p.TW - 1) / p.TW) * ((d.H + p.TH - 1) / p.TH) * ((d.D + t - 1) / t) *
+                                    ((d.Cout_pad + bn - 1) / bn);
+            const long long rounds = (tiles + sms - 1) / sms;
+            return (double)tiles / (double)(rounds * sms) * (t == td ? 1.0 : 0.93);   // halving TD costs ~7 % more slab traffic
+        };
+        if (fill(td / 2) > fill(td)) td /= 2;
+    }
     p.TD = td;
     p.acc_sets = (2 * td * bn <= 512) ? 2 : 1;
     if (td * bn > 512) return fail("TD*block_n exceeds TMEM");

@@ -16,7 +16,9 @@
 #include "ptx.cuh"
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <string>
 #include <vector>
 
 namespace pixie {
@@ -70,9 +72,9 @@ __device__ __forceinline__ void store_m3(float* p, int i, const M3& a) {
 
 struct Weights { int bx, by, bz; float fx[3]; float w[3][3]; float dw[3][3]; };   // [axis][node]
 
-__device__ __forceinline__ Weights bspline(const DevState& s, float px, float py, float pz) {
+__device__ __forceinline__ Weights bspline_t(float inv_dx, float px, float py, float pz) {
     Weights W;
-    const float g[3] = {px * s.inv_dx, py * s.inv_dx, pz * s.inv_dx};
+    const float g[3] = {px * inv_dx, py * inv_dx, pz * inv_dx};
     int b[3];
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
@@ -90,6 +92,7 @@ __device__ __forceinline__ Weights bspline(const DevState& s, float px, float py
     W.bx = b[0]; W.by = b[1]; W.bz = b[2];
     return W;
 }
+__device__ __forceinline__ Weights bspline(const DevState& s, float px, float py, float pz) { return bspline_t(s.inv_dx, px, py, pz); }
 
 // ------------------------------------------------------------------------------------------ p2g
 __global__ void __launch_bounds__(128)
@@ -439,6 +442,8 @@ __global__ void mpm_select_cyl_kernel(const DevState s, float3 point, float3 nor
     mask[p] = (vd < half_height && hd < radius) ? 1 : 0;
 }
 
+#include "mpm_tiled.cuh"
+
 }  // namespace
 
 // ============================================================================================ host
@@ -458,6 +463,26 @@ struct Mpm {
     double graph_dt = 0;
     bool graph_valid = false;
     std::string error;
+
+    // ---- tiled path (mpm_tiled.cuh)
+    bool tiled = true;
+    struct SortBuf {
+        float *x = nullptr, *v = nullptr, *C = nullptr, *F = nullptr, *Ft = nullptr, *stress = nullptr;
+        float *mass = nullptr, *vol = nullptr, *mu = nullptr, *lam = nullptr, *bulk = nullptr, *ys = nullptr;
+        int *material = nullptr, *selection = nullptr, *perm = nullptr;
+    } sb[2];
+    int cur = 0;                       // sb[cur] holds the live sorted state
+    int *keys = nullptr, *counts = nullptr, *off = nullptr, *cursor = nullptr, *occ = nullptr, *order = nullptr, *d_nocc = nullptr;
+    int nt = 0, ntiles = 0, n_occ = 0;
+    float4* mvbuf[3] = {nullptr, nullptr, nullptr};
+    int wbuf = 0;                      // buffer the next scatter writes (zero by invariant)
+    double* tslots = nullptr;          // [2] clock, by substep parity
+    float* pts = nullptr;              // [2][kMaxBC][3] moving BC points, by substep parity
+    int tpar = 0;
+    bool internal_valid = false;       // sorted state mirrors the caller's arrays (+ steps taken since)
+    bool user_stale = false;           // sorted state is ahead of the caller's arrays
+    int steps_since_sort = 0;
+    std::vector<void*> tiled_allocs;
 };
 
 static constexpr int kGraphSteps = 25;
@@ -485,6 +510,173 @@ static DevState make_state(Mpm* m) {
     return s;
 }
 
+void mpm_destroy(Mpm* m);
+int mpm_sync(Mpm* m, cudaStream_t st);
+
+// ---------------------------------------------------------------------------------- tiled path: host
+static constexpr int kResortEvery = 32;    // substeps between re-sorts (CFL keeps drift << one cell)
+
+template <typename T>
+static bool talloc(Mpm* m, T** p, size_t n) {
+    if (cudaMalloc(p, n * sizeof(T)) != cudaSuccess) return false;
+    cudaMemset(*p, 0, n * sizeof(T));
+    m->tiled_allocs.push_back(*p);
+    return true;
+}
+
+static int tiled_alloc_grid(Mpm* m) {
+    const size_t nodes = (size_t)m->n_grid * m->n_grid * m->n_grid;
+    m->nt = (m->n_grid + kTile - 1) / kTile;
+    m->ntiles = m->nt * m->nt * m->nt;
+    bool ok = true;
+    for (int i = 0; i < 3; ++i) ok = ok && talloc(m, &m->mvbuf[i], nodes);
+    ok = ok && talloc(m, &m->counts, (size_t)m->ntiles) && talloc(m, &m->off, (size_t)m->ntiles + 1) &&
+         talloc(m, &m->cursor, (size_t)m->ntiles) && talloc(m, &m->occ, (size_t)m->ntiles);
+    m->wbuf = 0;
+    return ok ? 0 : 1;
+}
+
+static int tiled_alloc(Mpm* m) {
+    const size_t n = (size_t)m->n;
+    bool ok = true;
+    for (int b = 0; b < 2; ++b) {
+        Mpm::SortBuf& s = m->sb[b];
+        ok = ok && talloc(m, &s.x, 3 * n) && talloc(m, &s.v, 3 * n) && talloc(m, &s.C, 9 * n) && talloc(m, &s.F, 9 * n) &&
+             talloc(m, &s.Ft, 9 * n) && talloc(m, &s.stress, 9 * n) && talloc(m, &s.mass, n) && talloc(m, &s.vol, n) &&
+             talloc(m, &s.mu, n) && talloc(m, &s.lam, n) && talloc(m, &s.bulk, n) && talloc(m, &s.ys, n) &&
+             talloc(m, &s.material, n) && talloc(m, &s.selection, n) && talloc(m, &s.perm, n);
+    }
+    ok = ok && talloc(m, &m->keys, n) && talloc(m, &m->order, n) && talloc(m, &m->d_nocc, (size_t)1) &&
+         talloc(m, &m->tslots, (size_t)2) && talloc(m, &m->pts, (size_t)2 * kMaxBC * 3);
+    if (!ok) return 1;
+    return tiled_alloc_grid(m);
+}
+
+// Builds the tile lists from positions `x` (n particles) and fills `order` (new position -> old position).
+static int tiled_build_order(Mpm* m, const float* x, cudaStream_t st) {
+    const float inv_dx = (float)((double)m->n_grid / (double)m->grid_lim);
+    cudaMemsetAsync(m->counts, 0, (size_t)m->ntiles * sizeof(int), st);
+    tiled_count_kernel<<<(m->n + 255) / 256, 256, 0, st>>>(x, m->n, inv_dx, m->n_grid, m->nt, m->keys, m->counts);
+    tiled_scan_kernel<<<1, 1024, 0, st>>>(m->counts, m->ntiles, m->off, m->cursor, m->occ, m->d_nocc);
+    tiled_place_kernel<<<(m->n + 255) / 256, 256, 0, st>>>(m->keys, m->n, m->cursor, m->order);
+    if (cudaMemcpyAsync(&m->n_occ, m->d_nocc, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess) return 1;
+    if (cudaStreamSynchronize(st) != cudaSuccess) return 1;
+    m->steps_since_sort = 0;
+    return 0;
+}
+
+static PermuteArgs permute_dst(Mpm* m, int b, PermuteArgs a) {
+    Mpm::SortBuf& d = m->sb[b];
+    a.ox = d.x; a.ov = d.v; a.oC = d.C; a.oF = d.F; a.oFt = d.Ft; a.ostress = d.stress; a.omass = d.mass; a.ovol = d.vol;
+    a.omu = d.mu; a.olam = d.lam; a.obulk = d.bulk; a.oys = d.ys; a.omaterial = d.material; a.oselection = d.selection; a.operm = d.perm;
+    return a;
+}
+
+// caller's arrays -> sorted state
+static int tiled_gather_from_user(Mpm* m, cudaStream_t st) {
+    auto f = [&](int id) { return reinterpret_cast<const float*>(m->fields[id]); };
+    if (tiled_build_order(m, f(PIXIE_MPM_X), st)) { m->error = "tile sort failed"; return 1; }
+    PermuteArgs a{};
+    a.order = m->order; a.n = m->n;
+    a.x = f(PIXIE_MPM_X); a.v = f(PIXIE_MPM_V); a.C = f(PIXIE_MPM_C); a.F = f(PIXIE_MPM_F); a.Ft = f(PIXIE_MPM_F_TRIAL);
+    a.stress = f(PIXIE_MPM_STRESS); a.mass = f(PIXIE_MPM_MASS); a.vol = f(PIXIE_MPM_VOL); a.mu = f(PIXIE_MPM_MU); a.lam = f(PIXIE_MPM_LAM);
+    a.bulk = f(PIXIE_MPM_BULK); a.ys = f(PIXIE_MPM_YIELD);
+    a.material = reinterpret_cast<const int*>(m->fields[PIXIE_MPM_MATERIAL]);
+    a.selection = reinterpret_cast<const int*>(m->fields[PIXIE_MPM_SELECTION]);
+    a.perm_src = nullptr;
+    m->cur = 0;
+    a = permute_dst(m, 0, a);
+    tiled_permute_kernel<<<(m->n + 255) / 256, 256, 0, st>>>(a);
+    m->internal_valid = true;
+    m->user_stale = false;
+    return cudaGetLastError() != cudaSuccess;
+}
+
+// re-sort the live sorted state (between two fused launches)
+static int tiled_resort(Mpm* m, cudaStream_t st) {
+    const Mpm::SortBuf& s = m->sb[m->cur];
+    if (tiled_build_order(m, s.x, st)) { m->error = "tile sort failed"; return 1; }
+    PermuteArgs a{};
+    a.order = m->order; a.n = m->n;
+    a.x = s.x; a.v = s.v; a.C = s.C; a.F = s.F; a.Ft = s.Ft; a.stress = s.stress; a.mass = s.mass; a.vol = s.vol; a.mu = s.mu;
+    a.lam = s.lam; a.bulk = s.bulk; a.ys = s.ys; a.material = s.material; a.selection = s.selection; a.perm_src = s.perm;
+    a = permute_dst(m, m->cur ^ 1, a);
+    tiled_permute_kernel<<<(m->n + 255) / 256, 256, 0, st>>>(a);
+    m->cur ^= 1;
+    return cudaGetLastError() != cudaSuccess;
+}
+
+// sorted state -> caller's arrays (if it is ahead); afterwards the caller may mutate its arrays, so the
+// sorted copy is considered out of date.
+int mpm_sync(Mpm* m, cudaStream_t st) {
+    if (!m->tiled) return 0;
+    if (m->user_stale) {
+        const Mpm::SortBuf& s = m->sb[m->cur];
+        auto f = [&](int id) { return reinterpret_cast<float*>(m->fields[id]); };
+        UnsortArgs a{};
+        a.perm = s.perm; a.n = m->n;
+        a.x = s.x; a.v = s.v; a.C = s.C; a.F = s.F; a.Ft = s.Ft; a.stress = s.stress; a.mu = s.mu; a.lam = s.lam; a.ys = s.ys;
+        a.ox = f(PIXIE_MPM_X); a.ov = f(PIXIE_MPM_V); a.oC = f(PIXIE_MPM_C); a.oF = f(PIXIE_MPM_F); a.oFt = f(PIXIE_MPM_F_TRIAL);
+        a.ostress = f(PIXIE_MPM_STRESS); a.omu = f(PIXIE_MPM_MU); a.olam = f(PIXIE_MPM_LAM); a.oys = f(PIXIE_MPM_YIELD);
+        tiled_unsort_kernel<<<(m->n + 255) / 256, 256, 0, st>>>(a);
+        m->user_stale = false;
+        if (cudaGetLastError() != cudaSuccess) { m->error = "unsort launch failed"; return 1; }
+    }
+    m->internal_valid = false;
+    return 0;
+}
+
+static TiledState tiled_state(Mpm* m) {
+    TiledState t{};
+    Mpm::SortBuf& s = m->sb[m->cur];
+    t.x = s.x; t.v = s.v; t.C = s.C; t.F = s.F; t.Ft = s.Ft; t.stress = s.stress; t.mass = s.mass; t.vol = s.vol; t.mu = s.mu; t.lam = s.lam;
+    t.bulk = s.bulk; t.yield_stress = s.ys; t.material = s.material; t.selection = s.selection; t.perm = s.perm;
+    t.occ = m->occ; t.tile_off = m->off; t.nt = m->nt;
+    t.bcs = m->d_bcs; t.n_bc = (int)m->bcs.size();
+    t.n = m->n; t.n_grid = m->n_grid;
+    t.dx = (float)((double)m->grid_lim / (double)m->n_grid);
+    t.inv_dx = (float)((double)m->n_grid / (double)m->grid_lim);
+    const pixie_mpm_params& q = m->params;
+    t.gx = q.gravity[0]; t.gy = q.gravity[1]; t.gz = q.gravity[2];
+    t.rpic_damping = q.rpic_damping; t.grid_v_damping_scale = q.grid_v_damping_scale; t.alpha = q.alpha; t.hardening = q.hardening;
+    t.xi = q.xi; t.plastic_viscosity = q.plastic_viscosity; t.softening = q.softening;
+    return t;
+}
+
+static void tiled_launch(Mpm* m, bool do_g2p, bool do_p2g, bool write_all, float dt, double dt_d, cudaStream_t st) {
+    TiledState t = tiled_state(m);
+    t.do_g2p = do_g2p; t.do_p2g = do_p2g; t.write_all = write_all;
+    // three rotating grid buffers; invariant: mvbuf[wbuf] is zero. Every launch reads the scatter completed by
+    // the previous scattering launch ((wbuf+2)%3), scatters into wbuf and clears the third buffer, which the
+    // launch before it read and which becomes the scatter target after this one.
+    t.mv_read = m->mvbuf[(m->wbuf + 2) % 3];
+    t.mv_write = m->mvbuf[m->wbuf];
+    t.mv_clear = m->mvbuf[(m->wbuf + 1) % 3];
+    t.time_in = m->tslots + m->tpar; t.time_out = m->tslots + (m->tpar ^ 1);
+    t.pts_in = m->pts + (size_t)m->tpar * kMaxBC * 3; t.pts_out = m->pts + (size_t)(m->tpar ^ 1) * kMaxBC * 3;
+    mpm_tiled_kernel<<<m->n_occ, kTiledThreads, 0, st>>>(t, dt, dt_d);
+    if (do_p2g) m->wbuf = (m->wbuf + 1) % 3;        // this launch filled wbuf; the next scatter goes to the buffer it cleared
+    if (do_g2p) m->tpar ^= 1;
+}
+
+static int mpm_step_tiled(Mpm* m, int n_substeps, double dt_d, cudaStream_t st) {
+    const float dt = (float)dt_d;
+    if (!m->internal_valid && tiled_gather_from_user(m, st)) return 1;
+    // prologue: scatter of the first substep (reads v, C, F_trial of the sorted state)
+    tiled_launch(m, false, true, n_substeps == 1, dt, dt_d, st);
+    for (int i = 0; i + 1 < n_substeps; ++i) {
+        if (m->steps_since_sort >= kResortEvery && tiled_resort(m, st)) return 1;
+        tiled_launch(m, true, true, i + 2 == n_substeps, dt, dt_d, st);    // g2p(i) + p2g(i+1)
+        ++m->steps_since_sort;
+    }
+    tiled_launch(m, true, false, true, dt, dt_d, st);                       // g2p of the last substep
+    ++m->steps_since_sort;
+    m->user_stale = true;
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { m->error = std::string("kernel launch failed: ") + cudaGetErrorString(e); return 1; }
+    return 0;
+}
+
 Mpm* mpm_create(int n_particles, int n_grid, float grid_lim, std::string& err) {
     if (n_particles <= 0 || n_grid <= 0) { err = "n_particles and n_grid must be positive"; return nullptr; }
     auto* m = new Mpm();
@@ -509,11 +701,14 @@ Mpm* mpm_create(int n_particles, int n_grid, float grid_lim, std::string& err) {
     cudaMemset(m->grid_mv, 0, nodes * sizeof(float4));
     cudaMemset(m->grid_v, 0, nodes * sizeof(float4));
     cudaMemset(m->d_time, 0, sizeof(double));
+    m->tiled = getenv("PIXIE_MPM_V1") == nullptr;
+    if (m->tiled && tiled_alloc(m)) { err = "cudaMalloc failed (tiled path)"; mpm_destroy(m); return nullptr; }
     return m;
 }
 
 void mpm_destroy(Mpm* m) {
     if (!m) return;
+    for (void* p : m->tiled_allocs) cudaFree(p);
     if (m->graph) cudaGraphExecDestroy(m->graph);
     cudaFree(m->grid_mv); cudaFree(m->grid_v); cudaFree(m->d_time); cudaFree(m->d_bcs);
     delete m;
@@ -521,11 +716,20 @@ void mpm_destroy(Mpm* m) {
 
 int mpm_bind(Mpm* m, int field, void* ptr) {
     if (field < 0 || field >= PIXIE_MPM_FIELD_COUNT) { m->error = "bad field id"; return 1; }
+    if (mpm_sync(m, 0)) return 1;          // flush results into the arrays bound so far before one of them changes
     m->fields[field] = ptr;
     m->graph_valid = false;
     return 0;
 }
 int mpm_set_params(Mpm* m, const pixie_mpm_params& p) {
+    if (mpm_sync(m, 0)) return 1;
+    if (p.n_grid != m->n_grid && m->tiled) {
+        // grid-sized tiled buffers are re-created with the grid (old ones are released with the handle)
+        const int old = m->n_grid;
+        m->n_grid = p.n_grid;
+        if (tiled_alloc_grid(m)) { m->n_grid = old; m->error = "cudaMalloc failed"; return 1; }
+        m->n_grid = old;
+    }
     if (p.n_grid != m->n_grid) {
         // set_parameters_dict re-allocates the grids when n_grid changes (mpm_solver_warp.py:318-343)
         cudaFree(m->grid_mv); cudaFree(m->grid_v);
@@ -555,15 +759,30 @@ int mpm_add_bc(Mpm* m, const pixie_mpm_bc& b) {
     d.surface_type = b.surface_type; d.reset = b.reset;
     d.rotation_scale = b.rotation_scale; d.translation_scale = b.translation_scale;
     d.mask = b.mask_dev;
+    if (mpm_sync(m, 0)) return 1;
     m->bcs.push_back(d);
     // append in place: the device table also holds the *moved* cuboid positions of earlier BCs
     cudaMemcpy(m->d_bcs + (m->bcs.size() - 1), &d, sizeof(DevBC), cudaMemcpyHostToDevice);
+    if (m->tiled) {
+        const size_t k = m->bcs.size() - 1;
+        cudaMemcpy(m->pts + 3 * k, d.point, 3 * sizeof(float), cudaMemcpyHostToDevice);
+        cudaMemcpy(m->pts + (size_t)kMaxBC * 3 + 3 * k, d.point, 3 * sizeof(float), cudaMemcpyHostToDevice);
+    }
     m->graph_valid = false;
     return 0;
 }
 int mpm_clear_bcs(Mpm* m) { m->bcs.clear(); m->graph_valid = false; return 0; }
-int mpm_set_time(Mpm* m, double t) { return cudaMemcpy(m->d_time, &t, sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess; }
-int mpm_get_time(Mpm* m, double* t) { return cudaMemcpy(t, m->d_time, sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess; }
+int mpm_set_time(Mpm* m, double t) {
+    if (m->tiled) {
+        const double both[2] = {t, t};
+        if (cudaMemcpy(m->tslots, both, sizeof(both), cudaMemcpyHostToDevice) != cudaSuccess) return 1;
+    }
+    return cudaMemcpy(m->d_time, &t, sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess;
+}
+int mpm_get_time(Mpm* m, double* t) {
+    const double* src = (m->tiled && !m->params.update_cov_with_F) ? m->tslots + m->tpar : m->d_time;
+    return cudaMemcpy(t, src, sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess;
+}
 
 static int check_bound(Mpm* m) {
     static const int need[] = {PIXIE_MPM_X, PIXIE_MPM_V, PIXIE_MPM_F, PIXIE_MPM_F_TRIAL, PIXIE_MPM_C, PIXIE_MPM_STRESS,
@@ -585,6 +804,13 @@ static void launch_substep(const DevState& s, float dt, double dt_d, cudaStream_
 
 int mpm_step(Mpm* m, int n_substeps, double dt_d, cudaStream_t st) {
     if (check_bound(m)) return 1;
+    if (n_substeps <= 0) return 0;
+    if (m->tiled && !m->params.update_cov_with_F) return mpm_step_tiled(m, n_substeps, dt_d, st);
+    if (m->tiled) {   // covariance-updating runs use the three-kernel path on the caller's arrays
+        if (mpm_sync(m, st)) return 1;
+        double t = 0; cudaMemcpy(&t, m->tslots + m->tpar, sizeof(double), cudaMemcpyDeviceToHost);
+        cudaMemcpy(m->d_time, &t, sizeof(double), cudaMemcpyHostToDevice);
+    }
     const float dt = (float)dt_d;
     const DevState s = make_state(m);
     int done = 0;
@@ -620,6 +846,7 @@ int mpm_step(Mpm* m, int n_substeps, double dt_d, cudaStream_t st) {
 }
 
 #define PIXIE_SIMPLE_LAUNCH(kernel)                                                         \
+    if (mpm_sync(m, st)) return 1;                                                          \
     const DevState s = make_state(m);                                                       \
     kernel<<<(m->n + 255) / 256, 256, 0, st>>>(s);                                          \
     const cudaError_t e = cudaGetLastError();                                               \
@@ -634,6 +861,7 @@ int mpm_compute_R_from_F(Mpm* m, cudaStream_t st) { PIXIE_SIMPLE_LAUNCH(mpm_R_fr
 
 int mpm_apply_additional_params(Mpm* m, const float* boxes_host, int n_boxes, cudaStream_t st) {
     if (n_boxes <= 0) return 0;
+    if (mpm_sync(m, st)) return 1;
     float* d = nullptr;
     if (cudaMalloc(&d, (size_t)n_boxes * 10 * 4) != cudaSuccess) { m->error = "cudaMalloc failed"; return 1; }
     cudaMemcpyAsync(d, boxes_host, (size_t)n_boxes * 10 * 4, cudaMemcpyHostToDevice, st);
@@ -646,12 +874,14 @@ int mpm_apply_additional_params(Mpm* m, const float* boxes_host, int n_boxes, cu
     return 0;
 }
 int mpm_select_box(Mpm* m, const float* point, const float* size, int* mask, cudaStream_t st) {
+    if (mpm_sync(m, st)) return 1;
     const DevState s = make_state(m);
     mpm_select_box_kernel<<<(m->n + 255) / 256, 256, 0, st>>>(s, make_float3(point[0], point[1], point[2]),
                                                               make_float3(size[0], size[1], size[2]), mask);
     return cudaGetLastError() != cudaSuccess;
 }
 int mpm_select_cylinder(Mpm* m, const float* point, const float* normal, float hh, float radius, int* mask, cudaStream_t st) {
+    if (mpm_sync(m, st)) return 1;
     const DevState s = make_state(m);
     mpm_select_cyl_kernel<<<(m->n + 255) / 256, 256, 0, st>>>(s, make_float3(point[0], point[1], point[2]),
                                                               make_float3(normal[0], normal[1], normal[2]), hh, radius, mask);

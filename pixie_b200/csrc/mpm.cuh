@@ -24,5 +24,6 @@ int mpm_apply_additional_params(Mpm* m, const float* boxes_host, int n_boxes, cu
 int mpm_select_box(Mpm* m, const float* point, const float* size, int* mask, cudaStream_t st);
 int mpm_select_cylinder(Mpm* m, const float* point, const float* normal, float hh, float radius, int* mask, cudaStream_t st);
 int mpm_grid_ptrs(Mpm* m, float** mv4, float** v4);
+int mpm_sync(Mpm* m, cudaStream_t st);
 const std::string& mpm_error(Mpm* m);
 }  // namespace pixie

@@ -172,6 +172,7 @@ struct Builder {
         d.NB = NB; d.D = d.H = d.W = sp_out; d.stride = stride; d.Cout = Cout;
         d.Cout_pad = (Cout + 15) / 16 * 16;
         d.split_k = 0;   // auto
+        if (Cout % 128 == 0 && sp_out >= 32 && !planar) d.block_n = 128;   // halves the A-slab traffic per output channel
         std::vector<const float*> wptr;
         std::vector<int> cin_real;
         std::vector<std::vector<float>> keep;

@@ -82,19 +82,13 @@ moments_kernel(const float* __restrict__ x, int V, int C, int vox_per_block, dou
 // mode NONE: cast only (raw copy).
 __global__ void __launch_bounds__(256)
 norm_act_kernel(NormArgs a) {
-    const int cols4 = a.C >> 2;
-    const int rows_par = 256 / cols4;
-    const int col = threadIdx.x % cols4;
-    const int row = threadIdx.x / cols4;
-    if (row >= rows_par) return;
+    // per-channel (mean, rstd, gamma, beta) once per block, in shared memory (C <= 1024)
+    __shared__ float s_mean[1024], s_rstd[1024], s_g[1024], s_b[1024];
     const int nb = blockIdx.y;
-    const int c = col * 4;
-    float mean[4] = {0, 0, 0, 0}, rstd[4] = {1, 1, 1, 1}, g[4] = {1, 1, 1, 1}, b[4] = {0, 0, 0, 0};
     if (a.mode != kNormNone) {
         const int cg = (a.mode == kNormGN) ? a.C / a.groups : 1;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int grp0 = ((c + j) / cg) * cg;
+        for (int ch = threadIdx.x; ch < a.C; ch += blockDim.x) {
+            const int grp0 = (ch / cg) * cg;
             double s = 0, q = 0;
             for (int k = 0; k < cg; ++k) {
                 s += a.stats[((size_t)nb * a.C + grp0 + k) * 2];
@@ -104,10 +98,23 @@ norm_act_kernel(NormArgs a) {
             const double m = s / n;
             double var = q / n - m * m;
             if (var < 0) var = 0;
-            mean[j] = (float)m;
-            rstd[j] = (float)(1.0 / sqrt(var + (double)a.eps));
-            if (a.mode == kNormGN) { g[j] = a.gamma[c + j]; b[j] = a.beta[c + j]; }
+            s_mean[ch] = (float)m;
+            s_rstd[ch] = (float)(1.0 / sqrt(var + (double)a.eps));
+            s_g[ch] = (a.mode == kNormGN) ? a.gamma[ch] : 1.f;
+            s_b[ch] = (a.mode == kNormGN) ? a.beta[ch] : 0.f;
         }
+        __syncthreads();
+    }
+    const int cols4 = a.C >> 2;
+    const int rows_par = 256 / cols4;
+    const int col = threadIdx.x % cols4;
+    const int row = threadIdx.x / cols4;
+    if (row >= rows_par) return;
+    const int c = col * 4;
+    float mean[4] = {0, 0, 0, 0}, rstd[4] = {1, 1, 1, 1}, g[4] = {1, 1, 1, 1}, b[4] = {0, 0, 0, 0};
+    if (a.mode != kNormNone) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { mean[j] = s_mean[c + j]; rstd[j] = s_rstd[c + j]; g[j] = s_g[c + j]; b[j] = s_b[c + j]; }
     }
     const int v0 = blockIdx.x * a.vox_per_block;
     const int v1 = min(a.V, v0 + a.vox_per_block);
@@ -247,7 +254,7 @@ int launch_pack_predictions(const float* seg, const float* cont, float* out, int
     return (int)cudaGetLastError();
 }
 
-static inline int vox_per_block_for(int V) { return V >= 4096 ? 256 : 64; }
+static inline int vox_per_block_for(int V) { return V >= 65536 ? 512 : (V >= 4096 ? 256 : 64); }
 
 int launch_moments(const float* x, int NB, int V, int C, double* stats, cudaStream_t st) {
     if (C % 4 || C / 4 > 256) return 1;

@@ -120,7 +120,7 @@ class MPM_Simulator_WARP:
         self._device = torch.device(device)
         n = self.n_particles
         dev = self._device
-        self._t = {}
+        self._tensors = {}
         with torch.cuda.device(dev):
             h = C.c_void_p()
             _lib.check(lib.pixie_mpm_create(n, int(n_grid), float(grid_lim), C.byref(h)))
@@ -169,8 +169,17 @@ class MPM_Simulator_WARP:
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self._device).cuda_stream)
 
+    @property
+    def _t(self):
+        """Particle / model tensors in the caller's order. The native solver keeps a cell-sorted private copy
+        between steps; any access goes through a sync (results written back, and — since the caller may now
+        modify the tensors in place like the reference's zero-copy exports allow — re-read at the next step)."""
+        if self._handle is not None:
+            _lib.check(_lib.load().pixie_mpm_sync(self._handle, self._stream()))
+        return self._tensors
+
     def _bind(self, fid: str, t: torch.Tensor):
-        self._t[fid] = t
+        self._tensors[fid] = t
         _lib.check(_lib.load().pixie_mpm_bind(self._handle, _lib.FIELDS[fid], C.c_void_p(t.data_ptr())))
 
     def _push_params(self):

@@ -1,0 +1,15 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 300 ./build/conv_test T_ > gpurun_out/conv_test.log 2>&1; grep -E "TIME|FAIL|SUMMARY" gpurun_out/conv_test.log | tail -12
+timeout 900 python -m pytest tests/test_gpu_unet.py -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit=$?"; tail -3 gpurun_out/pytest_gpu.log
+timeout 600 python bench.py --steps 5 --warmup 3 --precision fp16 --skip-cpu > gpurun_out/bench_fp16.json 2> gpurun_out/bench_fp16.err; echo "bench exit=$?"
+timeout 600 python bench.py --steps 5 --warmup 3 --skip-cpu > gpurun_out/bench_fp16x3.json 2> gpurun_out/bench_fp16x3.err; echo "bench exit=$?"
+python - <<'PY'
+import json
+for f in ['bench_fp16.json','bench_fp16x3.json']:
+    try:
+        d=json.loads(open('gpurun_out/'+f).read().strip().splitlines()[-1])
+        print(f, 'voxels/s=%.3e'%d['value'], 'unet_ms=%.2f'%d['unet_ms_per_scene'], 'conv frac=%.3f'%d['roofline']['frac'], 'e2e=%.3e'%d['e2e']['value'], d['unet_kernel_breakdown_ms'])
+    except Exception as e: print(f, 'ERR', e)
+PY
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv3d_igemm -s 150 -c 6 -o gpurun_out/prof_conv2 -f python scripts/profile_step.py fp16 1 > gpurun_out/ncu_conv2.log 2>&1; echo "ncu exit=$?"
