@@ -186,23 +186,26 @@ conv3d_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
                     const int kd_lo = max(0, pl - (t.tde - 1)), kd_hi = min(n_kd - 1, pl);
                     if (elect_one()) {
                         if (n_kh == 3) {
-                            for (int kd = kd_lo; kd <= kd_hi; ++kd) {
-                                const int d = pl - kd;
-                                const uint32_t acc = tmem_base + (uint32_t)((as * p.TD + d) * p.block_n);
-                                const uint32_t fresh = ((touched >> d) & 1u) ^ 1u;    // 1: accumulator d still empty
-                                touched |= (1u << d);
-                                const uint64_t da0 = desc_fixed | (uint64_t)(s16 & 0x3FFFu);
-                                const uint64_t db0 = desc_fixed | (uint64_t)((w16 + (uint32_t)(kd * 3) * tap_stride16) & 0x3FFFu);
+                            // Issue order: for each (kh, k-step) the SAME A operand is applied to the <=3 accumulators
+                            // (kd) it feeds. Consecutive MMAs therefore target different TMEM accumulators instead of
+                            // forming a 12-deep dependent chain on one of them.
+                            const uint64_t da0 = desc_fixed | (uint64_t)(s16 & 0x3FFFu);
+                            uint32_t fresh_mask = ~touched;                       // bit d set: accumulator d still empty
 #pragma unroll
-                                for (int kh = 0; kh < 3; ++kh) {
-                                    const uint64_t da = da0 + (uint64_t)(kh * kh_stride16);
-                                    const uint64_t db = db0 + (uint64_t)(kh * tap_stride16);
-                                    umma_f16(acc, da, db, idesc, (kh == 0) ? (fresh ^ 1u) : 1u);
-                                    umma_f16(acc, da + 2, db + 2, idesc, 1u);
-                                    umma_f16(acc, da + 4, db + 4, idesc, 1u);
-                                    umma_f16(acc, da + 6, db + 6, idesc, 1u);
+                            for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+                                for (int k4 = 0; k4 < 4; ++k4) {
+                                    const uint64_t da = da0 + (uint64_t)(kh * kh_stride16 + 2 * k4);
+                                    for (int kd = kd_lo; kd <= kd_hi; ++kd) {
+                                        const int d = pl - kd;
+                                        const uint32_t acc = tmem_base + (uint32_t)((as * p.TD + d) * p.block_n);
+                                        const uint64_t db = desc_fixed | (uint64_t)((w16 + (uint32_t)(kd * 3 + kh) * tap_stride16 + 2 * k4) & 0x3FFFu);
+                                        umma_f16(acc, da, db, idesc, ((fresh_mask >> d) & 1u) ^ 1u);
+                                    }
+                                    if (kh == 0 && k4 == 0) fresh_mask = 0;         // every accumulator of this slab has been written once
                                 }
                             }
+                            for (int kd = kd_lo; kd <= kd_hi; ++kd) touched |= (1u << (pl - kd));
                         } else {
                             for (int kd = kd_lo; kd <= kd_hi; ++kd) {
                                 const int d = pl - kd;

@@ -17,7 +17,7 @@
 constexpr int kTile = 4;                 // cells per tile edge
 constexpr int kHalo = kTile + 2;         // nodes per halo edge (quadratic B-spline: base .. base+2)
 constexpr int kHaloNodes = kHalo * kHalo * kHalo;
-constexpr int kTiledThreads = 256;
+constexpr int kTiledThreads = 128;
 
 struct TiledState {
     // sorted particle arrays (internal order); perm[p] = index in the caller's arrays
@@ -106,10 +106,13 @@ __device__ __forceinline__ void smem_add2(float* addr, float a, float b) {
 
 __device__ __forceinline__ float sel3(int i, float a, float b, float c) { return i == 0 ? a : (i == 1 ? b : c); }
 
-__global__ void __launch_bounds__(kTiledThreads)
+__global__ void __launch_bounds__(kTiledThreads, 4)
 mpm_tiled_kernel(const TiledState s, const float dt, const double dt_d) {
     __shared__ __align__(16) float4 sv[kHaloNodes];      // node velocities of this tile's halo (g2p source)
-    __shared__ __align__(16) float4 smv[kHaloNodes];     // {mv.xyz, m} accumulators (p2g target)
+    // {mv.xyz, m} accumulators (p2g target): one private copy per warp, so no shared-memory atomics are needed
+    // (fp32 smem atomics are ATOMS.CAS loops on sm_100: measured 7x slower than the global-red path they replaced);
+    // lanes of a warp that hit the same node in the same step are serialised with match.any
+    __shared__ __align__(16) float4 wacc[kTiledThreads / 32][kHaloNodes];
     const int tid = threadIdx.x;
     const int n = s.n_grid;
     const size_t nodes = (size_t)n * n * n;
@@ -131,16 +134,23 @@ mpm_tiled_kernel(const TiledState s, const float dt, const double dt_d) {
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (s.do_g2p && gx < n && gy < n && gz < n) v = node_velocity(s, s.mv_read[((size_t)gx * n + gy) * n + gz], gx, gy, gz, time, dt);
         sv[l] = v;
-        smv[l] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
+    for (int l = tid; l < (kTiledThreads / 32) * kHaloNodes; l += blockDim.x) (&wacc[0][0])[l] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
 
     const int p_begin = s.tile_off[tile], p_end = s.tile_off[tile + 1];
-    for (int p = p_begin + tid; p < p_end; p += blockDim.x) {
-        float px = s.x[3 * p], py = s.x[3 * p + 1], pz = s.x[3 * p + 2];
+    float4* my_acc = wacc[tid >> 5];
+    const unsigned lane = tid & 31, lt_mask = (1u << lane) - 1u;
+    for (int pb = p_begin; pb < p_end; pb += blockDim.x) {       // warp-uniform trip count (the scatter below is warp-collective)
+      const int p = pb + tid;
+      const bool active = p < p_end;
+      bool scatter = false;
+      float vx = 0.f, vy = 0.f, vz = 0.f, px = 0.f, py = 0.f, pz = 0.f, mass = 0.f, vol = 0.f;
+      M3 C = m3_zero(), tau = m3_zero();
+      if (active) do {
+        px = s.x[3 * p]; py = s.x[3 * p + 1]; pz = s.x[3 * p + 2];
         const bool simulated = s.selection[p] == 0;
-        float vx, vy, vz;
-        M3 C, Ft;
+        M3 Ft;
         if (s.do_g2p && simulated) {
             // ---- g2p (mpm_utils.py:412-463) from the shared halo; particles that drifted out of their tile
             //      since the last sort read the global grid instead
@@ -197,10 +207,10 @@ mpm_tiled_kernel(const TiledState s, const float dt, const double dt_d) {
             C = load_m3(s.C, p);
             Ft = load_m3(s.Ft, p);
         }
-        if (!s.do_p2g) continue;
+        if (!s.do_p2g) break;
 
         // ---- pre-p2g particle operations at the clock of the step being scattered (mpm_solver_warp.py:528-547)
-        const float mass = s.mass[p];
+        mass = s.mass[p];
         bool v_dirty = false;
         for (int k = 0; k < s.n_bc; ++k) {
             const DevBC& bc = s.bcs[k];
@@ -234,7 +244,7 @@ mpm_tiled_kernel(const TiledState s, const float dt, const double dt_d) {
             }
         }
         if (v_dirty && (!s.do_g2p || s.write_all)) { s.v[3 * p] = vx; s.v[3 * p + 1] = vy; s.v[3 * p + 2] = vz; }
-        if (!simulated) continue;
+        if (!simulated) break;
 
         // ---- compute_stress_from_F_trial (mpm_utils.py:467-526)
         const int material = s.material[p];
@@ -256,14 +266,16 @@ mpm_tiled_kernel(const TiledState s, const float dt, const double dt_d) {
         }
         store_m3(s.F, p, F);
         const float J = m3_det(F);
-        M3 tau = m3_zero();
         if (material == 6) tau = stress_water(J, s.bulk[p]);
-        else if (material != 4 && material >= 0 && material <= 5) {
+        else if (material == 0 || material == 5) {
+            M3 R;
+            if (polar_rotation(F, R)) tau = stress_fcr_R(F, R, J, mu, lam);
+            else { M3 U, V; V3 sig; svd3(F, U, sig, V); tau = stress_fcr(F, U, V, J, mu, lam); }
+        } else if (material >= 1 && material <= 3) {
             M3 U, V; V3 sig;
             svd3(F, U, sig, V);
-            if (material == 0 || material == 5) tau = stress_fcr(F, U, V, J, mu, lam);
-            else if (material == 1 || material == 3) tau = stress_stvk(F, U, V, sig, mu, lam);
-            else tau = stress_drucker_prager(F, U, V, sig, mu, lam);
+            if (material == 2) tau = stress_drucker_prager(F, U, V, sig, mu, lam);
+            else tau = stress_stvk(F, U, V, sig, mu, lam);
         }
         {
             const M3 tt = m3_t(tau);
@@ -272,8 +284,6 @@ mpm_tiled_kernel(const TiledState s, const float dt, const double dt_d) {
         }
         if (s.write_all) store_m3(s.stress, p, tau);
 
-        // ---- p2g_apic_with_stress (mpm_utils.py:338-394) into the shared halo
-        const Weights W = bspline_t(s.inv_dx, px, py, pz);
         {
             const float r = s.rpic_damping;
             const M3 Ct = m3_t(C);
@@ -282,46 +292,68 @@ mpm_tiled_kernel(const TiledState s, const float dt, const double dt_d) {
             for (int i = 0; i < 9; ++i) Cn.m[i] = (1.0f - r) * C.m[i] + r / 2.0f * (C.m[i] - Ct.m[i]);
             C = (r < -0.001f) ? m3_zero() : Cn;
         }
-        const float vol = s.vol[p];
+        vol = s.vol[p];
+        scatter = true;
+      } while (false);
+
+      // ---- p2g_apic_with_stress (mpm_utils.py:338-394) into the warp's private halo copy. Warp-collective, skipped by
+      //      warps without work. All lanes walk their 27 nodes in the same (i,j,k) order, so two lanes touch the same
+      //      node in the same step only if they share the base cell: one match.any per particle gives each lane its
+      //      turn, and plain read-modify-writes are race free.
+      if (s.do_p2g && __any_sync(0xffffffffu, scatter)) {
+        const Weights W = bspline_t(s.inv_dx, px, py, pz);
         const int lx = W.bx - bx0, ly = W.by - by0, lz = W.bz - bz0;
-        const bool in_tile = (unsigned)lx < (unsigned)kTile && (unsigned)ly < (unsigned)kTile && (unsigned)lz < (unsigned)kTile;
-        // lane-rotated node order: lanes of one warp start at different nodes, so particles sharing a cell
-        // (adjacent lanes after the sort) do not hammer the same shared-memory word in the same cycle
-        int nidx = (tid & 31) % 27;
-#pragma unroll 1
-        for (int it = 0; it < 27; ++it) {
-            const int i = nidx / 9, j = (nidx / 3) % 3, k = nidx % 3;
-            nidx = (nidx == 26) ? 0 : nidx + 1;
-            const float wxi = sel3(i, W.w[0][0], W.w[0][1], W.w[0][2]), wyj = sel3(j, W.w[1][0], W.w[1][1], W.w[1][2]),
-                        wzk = sel3(k, W.w[2][0], W.w[2][1], W.w[2][2]);
-            const float dxi = sel3(i, W.dw[0][0], W.dw[0][1], W.dw[0][2]), dyj = sel3(j, W.dw[1][0], W.dw[1][1], W.dw[1][2]),
-                        dzk = sel3(k, W.dw[2][0], W.dw[2][1], W.dw[2][2]);
-            const V3 dpos = {((float)i - W.fx[0]) * s.dx, ((float)j - W.fx[1]) * s.dx, ((float)k - W.fx[2]) * s.dx};
-            const float weight = wxi * wyj * wzk;
-            const V3 dweight = {dxi * wyj * wzk * s.inv_dx, wxi * dyj * wzk * s.inv_dx, wxi * wyj * dzk * s.inv_dx};
-            const V3 sd = m3_mulv(tau, dweight);
-            const V3 cd = m3_mulv(C, dpos);
-            const float wm = weight * mass;
-            const float ax = wm * (vx + cd.x) + dt * (-vol * sd.x);
-            const float ay = wm * (vy + cd.y) + dt * (-vol * sd.y);
-            const float az = wm * (vz + cd.z) + dt * (-vol * sd.z);
-            if (in_tile) {
-                float* node = reinterpret_cast<float*>(&smv[((lx + i) * kHalo + (ly + j)) * kHalo + (lz + k)]);
-                smem_add2(node, ax, ay);
-                smem_add2(node + 2, az, wm);
-            } else {
-                const int ix = W.bx + i, iy = W.by + j, iz = W.bz + k;
-                if ((unsigned)ix < (unsigned)n && (unsigned)iy < (unsigned)n && (unsigned)iz < (unsigned)n)
-                    ptx::red_add_v4(reinterpret_cast<float*>(s.mv_write + ((size_t)ix * n + iy) * n + iz), ax, ay, az, wm);
-            }
-        }
+        const bool in_tile = scatter && (unsigned)lx < (unsigned)kTile && (unsigned)ly < (unsigned)kTile && (unsigned)lz < (unsigned)kTile;
+        const int key = in_tile ? (lx * kTile + ly) * kTile + lz : (int)(kTile * kTile * kTile + lane);   // dummy keys are unique
+        const unsigned peers = __match_any_sync(0xffffffffu, key);
+        const int rank = __popc(peers & lt_mask);
+        const int rounds = __reduce_max_sync(0xffffffffu, __popc(peers));
+        float4* nbase = my_acc + (in_tile ? (lx * kHalo + ly) * kHalo + lz : 0);
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const V3 dpos = {((float)i - W.fx[0]) * s.dx, ((float)j - W.fx[1]) * s.dx, ((float)k - W.fx[2]) * s.dx};
+                    const float weight = W.w[0][i] * W.w[1][j] * W.w[2][k];
+                    const V3 dweight = {W.dw[0][i] * W.w[1][j] * W.w[2][k] * s.inv_dx,
+                                        W.w[0][i] * W.dw[1][j] * W.w[2][k] * s.inv_dx,
+                                        W.w[0][i] * W.w[1][j] * W.dw[2][k] * s.inv_dx};
+                    const V3 sd = m3_mulv(tau, dweight);
+                    const V3 cd = m3_mulv(C, dpos);
+                    const float wm = weight * mass;
+                    const float ax = wm * (vx + cd.x) + dt * (-vol * sd.x);
+                    const float ay = wm * (vy + cd.y) + dt * (-vol * sd.y);
+                    const float az = wm * (vz + cd.z) + dt * (-vol * sd.z);
+                    float4* node = nbase + (i * kHalo + j) * kHalo + k;
+                    for (int rr = 0; rr < rounds; ++rr) {
+                        if (in_tile && rank == rr) {
+                            float4 a = *node;
+                            a.x += ax; a.y += ay; a.z += az; a.w += wm;
+                            *node = a;
+                        }
+                        __syncwarp();
+                    }
+                    if (scatter && !in_tile) {
+                        const int ix = W.bx + i, iy = W.by + j, iz = W.bz + k;
+                        if ((unsigned)ix < (unsigned)n && (unsigned)iy < (unsigned)n && (unsigned)iz < (unsigned)n)
+                            ptx::red_add_v4(reinterpret_cast<float*>(s.mv_write + ((size_t)ix * n + iy) * n + iz), ax, ay, az, wm);
+                    }
+                }
+      }
     }
 
     // ---- flush the tile's halo: one vector red per touched node
     if (s.do_p2g) {
         __syncthreads();
         for (int l = tid; l < kHaloNodes; l += blockDim.x) {
-            const float4 a = smv[l];
+            float4 a = wacc[0][l];
+#pragma unroll
+            for (int w = 1; w < kTiledThreads / 32; ++w) {
+                const float4 b = wacc[w][l];
+                a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+            }
             if (a.w != 0.f || a.x != 0.f || a.y != 0.f || a.z != 0.f) {
                 const int i = l / (kHalo * kHalo), j = (l / kHalo) % kHalo, k = l % kHalo;
                 const int gx = bx0 + i, gy = by0 + j, gz = bz0 + k;

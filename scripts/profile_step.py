@@ -16,6 +16,6 @@ feat = bench.make_features(a.grid, a.channels, 1).cuda()
 solver = bench.setup_solver(bench.make_mpm_scene(a.particles, a.mpm_grid, 0), a.mpm_grid, "cuda:0")
 for _ in range(2):
     pred.predict(feat)
-    for _ in range(nsub): solver.p2g2p(0, 1e-4)      # direct launches (ncu does not see inside graph replays the same way)
+    solver.p2g2p_n(nsub, 1e-4)
 torch.cuda.synchronize()
 print("done")
