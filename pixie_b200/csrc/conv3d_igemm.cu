@@ -77,6 +77,28 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvKernelParams& p, int 
 
 }  // namespace
 
+// One input slab of a 3x3x3 stride-1 phase: 12 MMAs (3 kh x 4 K steps of 16) of N = nblk*BN columns into the nblk adjacent
+// accumulators starting at acc0. Everything that depends on (kh, k4) is a compile-time immediate so the single issuing
+// thread spends ~4 instructions per tcgen05.mma; with run-time strides it spends ~20 and becomes the kernel's bottleneck
+// (r01: 240 instructions per slab at ~7 cycles each vs 12 x 96 tensor-pipe cycles).
+template <int BN, int TWv>
+__device__ __forceinline__ void issue_slab_3x3(uint32_t acc0, uint32_t a_lo0, uint32_t b_lo0, uint32_t hi, uint32_t idA,
+                                               uint32_t id_old, uint32_t id1, int nold, bool fresh) {
+    constexpr uint32_t kKh = (uint32_t)(TWv * 128) >> 4, kTap = (uint32_t)(BN * 128) >> 4;
+    if (fresh) {
+        // the newest plane's accumulator is overwritten by its first MMA, the older planes accumulate
+        if (nold > 0) umma_f16_lohi<true>(acc0, a_lo0, b_lo0, hi, id_old);
+        umma_f16_lohi<false>(acc0 + (uint32_t)(nold * BN), a_lo0, b_lo0 + (uint32_t)nold * kTap, hi, id1);
+    } else {
+        umma_f16_lohi<true>(acc0, a_lo0, b_lo0, hi, idA);
+    }
+#pragma unroll
+    for (int i = 1; i < 12; ++i) {
+        const uint32_t kh = (uint32_t)(i >> 2), k4 = (uint32_t)(i & 3);
+        umma_f16_lohi<true>(acc0, a_lo0 + kh * kKh + 2u * k4, b_lo0 + kh * 3u * kTap + 2u * k4, hi, idA);
+    }
+}
+
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv3d_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -119,6 +141,7 @@ conv3d_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
     if (warp == 0) {
         // ================================================================ TMA producer (warp-uniform, one elected lane issues)
         int ws = 0, wph = 0, ss = 0, sph = 0;
+        int wcount = 0, scount = 0;     // bring-up only (debug_flags bit 1: stop re-loading once every stage was filled)
         bool ok = true;
         for (int wi = blockIdx.x; wi < total_items && ok; wi += gridDim.x) {
             const TileCoord t = decode_tile(p, wi);
@@ -127,13 +150,15 @@ conv3d_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
                 const int ntaps = P.n_kh * P.n_kd;
                 ok = mbar_wait(&ctl->wempty[ws], wph ^ 1, abort_flag);
                 if (!ok) break;
-                if (elect_one()) {
+                if ((p.debug_flags & 2) && wcount >= p.w_stages) { if (elect_one()) mbar_arrive(&ctl->wfull[ws]); }
+                else if (elect_one()) {
                     mbar_expect_tx(&ctl->wfull[ws], (uint32_t)(ntaps * p.block_n * 128));
                     uint8_t* wdst = w_smem + (size_t)ws * p.w_stage_bytes;
                     for (int tap = 0; tap < ntaps; ++tap)
                         tma_load_2d(wdst + (size_t)tap * p.block_n * 128, &p.tmB, &ctl->wfull[ws],
                                     (P.wtile_base + tap) * 64, t.n0);
                 }
+                ++wcount;
                 if (++ws == p.w_stages) { ws = 0; wph ^= 1; }
 
                 const int nplanes = t.tde + P.n_kd - 1;
@@ -141,12 +166,14 @@ conv3d_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
                 for (int pl = 0; pl < nplanes && ok; ++pl) {
                     ok = mbar_wait(&ctl->sempty[ss], sph ^ 1, abort_flag);
                     if (!ok) break;
-                    if (elect_one()) {
+                    if ((p.debug_flags & 2) && scount >= p.s_stages) { if (elect_one()) mbar_arrive(&ctl->sfull[ss]); }
+                    else if (elect_one()) {
                         mbar_expect_tx(&ctl->sfull[ss], slab_bytes);
                         tma_load_5d(s_smem + (size_t)ss * p.s_stage_bytes, &p.tmA[P.src],
                                     &ctl->sfull[ss], (int)P.c0, t.w0 * p.stride + P.dw,
                                     t.h0 * p.stride + P.dh0, (t.d0 + pl) * p.stride + P.dd0, t.nb);
                     }
+                    ++scount;
                     if (++ss == p.s_stages) { ss = 0; sph ^= 1; }
                 }
             }
@@ -158,8 +185,12 @@ conv3d_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
         // elected lane. A single divergent thread costs ~25 scalar instructions per MMA (ncu: tensor pipe
         // 23 % busy, issue thread never waiting).
         int ws = 0, wph = 0, ss = 0, sph = 0, as = 0, aph = 0;
-        const uint32_t idesc = make_idesc_f16(128, (uint32_t)p.block_n);
+        const int max_blk = min(3, 256 / p.block_n);                             // accumulator blocks one MMA may span
+        const uint32_t idesc1 = make_idesc_f16(128, (uint32_t)p.block_n), idesc2 = make_idesc_f16(128, (uint32_t)(2 * p.block_n)),
+                       idesc3 = make_idesc_f16(128, (uint32_t)(3 * p.block_n));
         const uint64_t desc_fixed = (make_sw128_desc(0, 1024) ^ p.desc_xor);   // everything but the start address
+        const uint32_t desc_lo = (uint32_t)desc_fixed, desc_hi = (uint32_t)(desc_fixed >> 32);
+        const bool fast3 = (p.block_n == 64 || p.block_n == 128) && (p.TW == 16 || p.TW == 8);
         const uint32_t w_base0 = smem_u32(w_smem), s_base0 = smem_u32(s_smem);
         const uint32_t kh_stride16 = (uint32_t)(p.TW * 128) >> 4;             // descriptor units of 16 B
         const uint32_t tap_stride16 = (uint32_t)(p.block_n * 128) >> 4;
@@ -169,7 +200,6 @@ conv3d_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
             ok = mbar_wait(&ctl->tempty[as], aph ^ 1, abort_flag);
             if (!ok) break;
             tc_fence_after();
-            uint32_t touched = 0;
             for (int ph = t.ph_begin; ph < t.ph_end && ok; ++ph) {
                 const ConvPhase P = p.phases[ph];
                 const int n_kd = P.n_kd, n_kh = P.n_kh;
@@ -182,47 +212,53 @@ conv3d_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
                     if (!ok) break;
                     tc_fence_after();
                     const uint32_t s16 = (s_base0 + (uint32_t)(ss * p.s_stage_bytes)) >> 4;
-                    // taps served by this slab: kd in [kd_lo, kd_hi] (accumulator d = pl - kd must exist)
-                    const int kd_lo = max(0, pl - (t.tde - 1)), kd_hi = min(n_kd - 1, pl);
+                    // This slab (input plane pl) feeds output planes d = pl - kd: accumulators d_min..d_max are ADJACENT
+                    // column blocks of TMEM and the matching weight tiles (kd = kd_hi..kd_lo) are adjacent row blocks of
+                    // the B stage, so one MMA of N = nblk*block_n covers them all (tcgen05.mma has a ~56-cycle floor per
+                    // 128xNx16 instruction for N <= 112 and runs at N/2 cycles from N = 128 up: mma_bench.cu).
+                    const int d_min = max(0, pl - (n_kd - 1)), d_max = min(t.tde - 1, pl);
+                    const int nblk = d_max - d_min + 1, kd_hi = pl - d_min;
+                    const bool fresh = (ph == t.ph_begin) && (d_max == pl);   // plane pl's accumulator is first touched here
                     if (elect_one()) {
-                        if (n_kh == 3) {
-                            // Issue order: for each (kh, k-step) the SAME A operand is applied to the <=3 accumulators
-                            // (kd) it feeds. Consecutive MMAs therefore target different TMEM accumulators instead of
-                            // forming a 12-deep dependent chain on one of them.
-                            const uint64_t da0 = desc_fixed | (uint64_t)(s16 & 0x3FFFu);
-                            uint32_t fresh_mask = ~touched;                       // bit d set: accumulator d still empty
-#pragma unroll
-                            for (int kh = 0; kh < 3; ++kh) {
-#pragma unroll
-                                for (int k4 = 0; k4 < 4; ++k4) {
-                                    const uint64_t da = da0 + (uint64_t)(kh * kh_stride16 + 2 * k4);
-                                    for (int kd = kd_lo; kd <= kd_hi; ++kd) {
-                                        const int d = pl - kd;
-                                        const uint32_t acc = tmem_base + (uint32_t)((as * p.TD + d) * p.block_n);
-                                        const uint64_t db = desc_fixed | (uint64_t)((w16 + (uint32_t)(kd * 3 + kh) * tap_stride16 + 2 * k4) & 0x3FFFu);
-                                        umma_f16(acc, da, db, idesc, ((fresh_mask >> d) & 1u) ^ 1u);
-                                    }
-                                    if (kh == 0 && k4 == 0) fresh_mask = 0;         // every accumulator of this slab has been written once
-                                }
+                        const uint32_t acc0 = tmem_base + (uint32_t)((as * p.TD + d_min) * p.block_n);
+                        const uint32_t wblk0 = (uint32_t)(n_kd - 1 - kd_hi);
+                        const int nold0 = fresh ? nblk - 1 : nblk;
+                        if (n_kh == 3 && n_kd == 3 && nblk <= max_blk && fast3) {
+                            const uint32_t idA = nblk == 1 ? idesc1 : (nblk == 2 ? idesc2 : idesc3);
+                            const int nold = nblk - 1;
+                            const uint32_t id_old = nold == 1 ? idesc1 : idesc2;
+                            const uint32_t a_lo0 = desc_lo | (s16 & 0x3FFFu);
+                            const uint32_t b_lo0 = desc_lo | ((w16 + wblk0 * tap_stride16) & 0x3FFFu);
+                            if (p.block_n == 64) {
+                                if (p.TW == 16) issue_slab_3x3<64, 16>(acc0, a_lo0, b_lo0, desc_hi, idA, id_old, idesc1, nold, fresh);
+                                else issue_slab_3x3<64, 8>(acc0, a_lo0, b_lo0, desc_hi, idA, id_old, idesc1, nold, fresh);
+                            } else {
+                                if (p.TW == 16) issue_slab_3x3<128, 16>(acc0, a_lo0, b_lo0, desc_hi, idA, id_old, idesc1, nold, fresh);
+                                else issue_slab_3x3<128, 8>(acc0, a_lo0, b_lo0, desc_hi, idA, id_old, idesc1, nold, fresh);
                             }
-                            for (int kd = kd_lo; kd <= kd_hi; ++kd) touched |= (1u << (pl - kd));
-                        } else {
-                            for (int kd = kd_lo; kd <= kd_hi; ++kd) {
-                                const int d = pl - kd;
-                                const uint32_t acc = tmem_base + (uint32_t)((as * p.TD + d) * p.block_n);
-                                const uint32_t fresh = ((touched >> d) & 1u) ^ 1u;
-                                touched |= (1u << d);
-                                const uint64_t da = desc_fixed | (uint64_t)(s16 & 0x3FFFu);
-                                const uint64_t db = desc_fixed | (uint64_t)((w16 + (uint32_t)kd * tap_stride16) & 0x3FFFu);
-                                umma_f16(acc, da, db, idesc, fresh ^ 1u);
-                                umma_f16(acc, da + 2, db + 2, idesc, 1u);
-                                umma_f16(acc, da + 4, db + 4, idesc, 1u);
-                                umma_f16(acc, da + 6, db + 6, idesc, 1u);
+                        } else
+                        for (int kh = 0; kh < n_kh; ++kh) {
+                            const uint32_t a16 = s16 + (uint32_t)kh * kh_stride16;
+                            const uint32_t b16 = w16 + ((uint32_t)kh * (uint32_t)n_kd + wblk0) * tap_stride16;
+#pragma unroll
+                            for (int k4 = 0; k4 < 4; ++k4) {
+                                const uint64_t da = desc_fixed | (uint64_t)((a16 + 2u * k4) & 0x3FFFu);
+                                const bool split_new = fresh && kh == 0 && k4 == 0;
+                                const int nold = split_new ? nold0 : nblk;
+                                for (int b = 0; b < nold; b += max_blk) {
+                                    const int cnt = min(max_blk, nold - b);
+                                    const uint32_t idn = (cnt == 1) ? idesc1 : (cnt == 2 ? idesc2 : idesc3);
+                                    const uint64_t db = desc_fixed | (uint64_t)((b16 + (uint32_t)b * tap_stride16 + 2u * k4) & 0x3FFFu);
+                                    umma_f16(acc0 + (uint32_t)(b * p.block_n), da, db, idn, 1u);
+                                }
+                                if (split_new) {
+                                    const uint64_t db = desc_fixed | (uint64_t)((b16 + (uint32_t)(nblk - 1) * tap_stride16 + 2u * k4) & 0x3FFFu);
+                                    umma_f16(acc0 + (uint32_t)((nblk - 1) * p.block_n), da, db, idesc1, 0u);
+                                }
                             }
                         }
                         umma_commit(&ctl->sempty[ss]);        // slab slot free once these MMAs retire
                     }
-                    for (int kd = kd_lo; kd <= kd_hi; ++kd) touched |= (1u << (pl - kd));   // keep the mask warp-uniform
                     if (++ss == p.s_stages) { ss = 0; sph ^= 1; }
                 }
                 if (elect_one()) umma_commit(&ctl->wempty[ws]);
@@ -241,14 +277,30 @@ conv3d_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
         bool ok = true;
         const long long DHW = (long long)p.D * p.H * p.W;
         const bool do_stats = p.stats != nullptr;
+        const bool scalar_stats = do_stats && p.stats_scalar;     // consumer only needs the per-item totals (LayerNorm)
         float* my_stats = stats_sm + (size_t)(warp - 2) * 2 * kStatsMaxC;
         const int et = threadIdx.x - 64;        // 0..127 among the epilogue threads
         int stats_nb = -1;
-        if (do_stats) {
+        double tot_s = 0.0, tot_q = 0.0;        // scalar mode: this thread's running totals
+        if (do_stats && !scalar_stats) {
             for (int i = lane; i < 2 * kStatsMaxC; i += 32) my_stats[i] = 0.f;
             __syncwarp();
         }
         auto flush_stats = [&](int nb) {
+            if (scalar_stats) {
+                // totals go to channel 0's slot; the LayerNorm consumer sums the [Cout][2] row anyway
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) {
+                    tot_s += __shfl_xor_sync(0xffffffffu, tot_s, off);
+                    tot_q += __shfl_xor_sync(0xffffffffu, tot_q, off);
+                }
+                if (lane == 0) {
+                    atomicAdd(p.stats + (size_t)nb * p.Cout * 2, tot_s);
+                    atomicAdd(p.stats + (size_t)nb * p.Cout * 2 + 1, tot_q);
+                }
+                tot_s = 0.0; tot_q = 0.0;
+                return;
+            }
             // all 4 epilogue warps: fold the warp-private partial sums into the global fp64 accumulators
             asm volatile("bar.sync 1, 128;" ::: "memory");
             for (int ch = et; ch < p.Cout; ch += 128) {
@@ -265,6 +317,28 @@ conv3d_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
             for (int i = lane; i < 2 * kStatsMaxC; i += 32) my_stats[i] = 0.f;
             __syncwarp();
         };
+        // f[0..15] = final values of 16 channels of this thread's voxel row (zero where invalid)
+        auto add_stats16 = [&](float (&f)[16], int ch0) {
+            float sq[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) sq[j] = f[j] * f[j];
+            if (scalar_stats) {
+                float s = 0.f, q2 = 0.f;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) { s += f[j]; q2 += sq[j]; }
+                tot_s += (double)s; tot_q += (double)q2;
+                return;
+            }
+            const float s1 = warp_colsum16(f, lane);
+            const float s2 = warp_colsum16(sq, lane);
+            const int chn = ch0 + stats_channel_of_lane(lane);
+            if ((lane & 1) == 0 && chn < p.Cout) {
+                my_stats[chn] += s1;
+                my_stats[kStatsMaxC + chn] += s2;
+            }
+            __syncwarp();
+        };
+        const bool wide_ok = !p.out_planar && ((p.out_ld & 3) == 0) && ((p.out_c0 & 3) == 0);
         for (int wi = blockIdx.x; wi < total_items && ok; wi += gridDim.x) {
             const TileCoord t = decode_tile(p, wi);
             ok = mbar_wait(&ctl->tfull[as], aph, abort_flag);
@@ -277,11 +351,82 @@ conv3d_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
             const int hh = t.h0 + th, ww = t.w0 + tw;
             const bool row_ok = (hh < p.H) && (ww < p.W);
             const bool first_split = (t.split == 0);
-            for (int d = 0; d < t.tde; ++d) {
+            for (int d = 0; d < t.tde && !(p.debug_flags & 1); ++d) {
                 const long long vox = ((long long)(t.d0 + d) * p.H + hh) * p.W + ww;   // inside batch item
                 const uint32_t acc = tmem_base + ((uint32_t)(q * 32) << 16) +
                                      (uint32_t)((as * p.TD + d) * p.block_n);
-                for (int c = 0; c < p.block_n; c += 16) {
+                int c = 0;
+                // ---- wide path: 64 channels per step. One warp per scheduler means nothing hides latency but the
+                // warp's own ILP: both TMEM loads and all 16 residual loads are in flight before the first use.
+                for (; wide_ok && c + 64 <= p.block_n && t.n0 + c + 64 <= p.Cout; c += 64) {
+                    const int ch0 = t.n0 + c;
+                    uint32_t v[64];
+                    tmem_ld32(acc + (uint32_t)c, v);
+                    tmem_ld32(acc + (uint32_t)c + 32u, v + 32);
+                    const long long base = ((long long)t.nb * DHW + vox) * p.out_ld + p.out_c0 + ch0;
+                    const bool use_res = row_ok && first_split && p.residual != nullptr;
+                    float4 rv[16];
+                    if (use_res) {
+                        const float4* rp = reinterpret_cast<const float4*>(p.residual + base);
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) rv[j] = __ldg(rp + j);
+                    }
+                    float4 bv[16];
+                    const bool use_bias = first_split && p.bias != nullptr;
+                    if (use_bias) {
+                        const float4* bp = reinterpret_cast<const float4*>(p.bias + ch0);
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) bv[j] = __ldg(bp + j);
+                    }
+                    tmem_ld_wait();
+                    float f[64];
+#pragma unroll
+                    for (int j = 0; j < 64; ++j) f[j] = __uint_as_float(v[j]);
+                    if (use_bias) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            f[4 * j + 0] += bv[j].x; f[4 * j + 1] += bv[j].y;
+                            f[4 * j + 2] += bv[j].z; f[4 * j + 3] += bv[j].w;
+                        }
+                    }
+                    if (use_res) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            f[4 * j + 0] += rv[j].x; f[4 * j + 1] += rv[j].y;
+                            f[4 * j + 2] += rv[j].z; f[4 * j + 3] += rv[j].w;
+                        }
+                    }
+                    if (row_ok) {
+                        if (p.atomic_out) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                red_add_v4(p.out + base + 4 * j, f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                        } else {
+                            float4* op = reinterpret_cast<float4*>(p.out + base);
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                        }
+                    }
+                    if (do_stats) {
+                        if (scalar_stats) {
+                            float s = 0.f, q2 = 0.f;
+#pragma unroll
+                            for (int j = 0; j < 64; ++j) { s += f[j]; q2 = fmaf(f[j], f[j], q2); }
+                            if (row_ok) { tot_s += (double)s; tot_q += (double)q2; }
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                float g[16];
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) g[j] = row_ok ? f[16 * k + j] : 0.f;
+                                add_stats16(g, ch0 + 16 * k);
+                            }
+                        }
+                    }
+                }
+                // ---- generic path: 16 channels per step (ragged Cout, planar outputs, narrow tiles)
+                for (; c < p.block_n; c += 16) {
                     uint32_t v[16];
                     tmem_ld16(acc + (uint32_t)c, v);
                     tmem_ld_wait();
@@ -347,21 +492,10 @@ conv3d_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
                             }
                         }
                         if (do_stats) {
-                            // f[] now holds the final output values of this voxel row: column sums over the warp
-                            float sq[16];
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) {
+                            for (int j = 0; j < 16; ++j)
                                 if (!row_ok || ch0 + j >= p.Cout) f[j] = 0.f;
-                                sq[j] = f[j] * f[j];
-                            }
-                            const float s1 = warp_colsum16(f, lane);
-                            const float s2 = warp_colsum16(sq, lane);
-                            const int chn = ch0 + stats_channel_of_lane(lane);
-                            if ((lane & 1) == 0 && chn < p.Cout) {
-                                my_stats[chn] += s1;
-                                my_stats[kStatsMaxC + chn] += s2;
-                            }
-                            __syncwarp();
+                            add_stats16(f, ch0);
                         }
                     }
                 }
@@ -481,8 +615,11 @@ void conv_pack_weights(const ConvDesc& d, const std::vector<const float*>& seg_w
         } else if (d.stride == 1) {
             for (int c = 0; c < chunks; ++c)
                 for (int kw = 0; kw < 3; ++kw) {
+                    // tile order inside the phase: kh major, then kd = 2,1,0 — the three kd tiles of one kh are
+                    // contiguous so that ONE MMA with N = 3*block_n feeds the accumulators of output planes
+                    // p-2, p-1, p (which are adjacent TMEM column blocks)
                     for (int kd = 0; kd < 3; ++kd)
-                        for (int kh = 0; kh < 3; ++kh) put(wtile + kd * 3 + kh, c, kd, kh, kw);
+                        for (int kh = 0; kh < 3; ++kh) put(wtile + kh * 3 + (2 - kd), c, kd, kh, kw);
                     wtile += 9;
                 }
         } else {
@@ -649,7 +786,9 @@ int conv_plan_create(const ConvDesc& d, int* d_err_flag, ConvPlan& plan, char* e
     p.out_ld = d.out_ld ? d.out_ld : d.Cout; p.out_c0 = d.out_c0; p.out_planar = d.out_planar;
     p.err_flag = d_err_flag;
     p.stats = plan.fused_stats ? d.stats : nullptr;
+    p.stats_scalar = d.stats_scalar ? 1 : 0;
     p.desc_xor = 0;
+    p.debug_flags = 0;
     plan.out_bytes = d.out_planar ? (size_t)d.NB * d.Cout * d.D * d.H * d.W * 4
                                   : (size_t)d.NB * d.D * d.H * d.W * p.out_ld * 4;
 

@@ -131,6 +131,8 @@ int main(int argc, char** argv) {
         CK(cudaMalloc(&d_stats, (size_t)c.NB * c.Cout * 2 * sizeof(double)));
         CK(cudaMemset(d_stats, 0, (size_t)c.NB * c.Cout * 2 * sizeof(double)));
         d.stats = d_stats;
+        const bool scalar_stats = getenv("CONV_TEST_SCALAR_STATS") != nullptr;   // totals-only mode of the fused statistics
+        d.stats_scalar = scalar_stats;
 
         CK(cudaMemset(d_err, 0, sizeof(int)));
         ConvPlan plan;
@@ -141,6 +143,7 @@ int main(int argc, char** argv) {
             continue;
         }
         plan.p.desc_xor = hi_xor;
+        if (getenv("CONV_DEBUG")) plan.p.debug_flags = atoi(getenv("CONV_DEBUG"));
         printf("[%s] grid=%d smem=%d bn=%d TD=%d TW=%d TH=%d acc_sets=%d w_stages=%d s_stages=%d phases=%d split=%d\n",
                c.name.c_str(), plan.grid, plan.smem_bytes, plan.p.block_n, plan.p.TD, plan.p.TW, plan.p.TH,
                plan.p.acc_sets, plan.p.w_stages, plan.p.s_stages, plan.p.n_phases, plan.p.split_k);
@@ -223,16 +226,27 @@ int main(int argc, char** argv) {
             std::vector<double> h_stats((size_t)c.NB * c.Cout * 2);
             CK(cudaMemcpy(h_stats.data(), d_stats, h_stats.size() * sizeof(double), cudaMemcpyDeviceToHost));
             const size_t vpb = (size_t)Do * Do * Do;
-            for (int nb = 0; nb < c.NB; ++nb)
+            for (int nb = 0; nb < c.NB; ++nb) {
+                double ts = 0, tq = 0, gts = 0, gtq = 0;
                 for (int co = 0; co < c.Cout; ++co) {
                     double s = 0, q = 0;
                     for (size_t v = 0; v < vpb; ++v) { const double x = h_out[((size_t)nb * vpb + v) * c.Cout + co]; s += x; q += x * x; }
                     const double gs = h_stats[((size_t)nb * c.Cout + co) * 2], gq = h_stats[((size_t)nb * c.Cout + co) * 2 + 1];
+                    ts += s; tq += q; gts += gs; gtq += gq;
+                    if (scalar_stats) {
+                        if (co > 0 && (gs != 0 || gq != 0)) ++stats_bad;      // totals live in channel 0's slot only
+                        continue;
+                    }
                     if (std::fabs(gs - s) > 1e-3 * (1 + std::fabs(s)) + 1e-4 * std::sqrt(q * vpb) || std::fabs(gq - q) > 1e-4 * (1 + q)) {
                         if (stats_bad < 3) printf("   stats mismatch nb=%d co=%d: sum %g vs %g, sumsq %g vs %g\n", nb, co, gs, s, gq, q);
                         ++stats_bad;
                     }
                 }
+                if (scalar_stats && (std::fabs(gts - ts) > 1e-5 * std::sqrt(tq * vpb * c.Cout) + 1e-6 || std::fabs(gtq - tq) > 1e-6 * (1 + tq))) {
+                    printf("   scalar stats mismatch nb=%d: sum %.9g vs %.9g, sumsq %.9g vs %.9g\n", nb, gts, ts, gtq, tq);
+                    ++stats_bad;
+                }
+            }
             printf("[%s] fused stats checked: bad=%zu\n", c.name.c_str(), stats_bad);
         }
         const bool pass = (bad == 0 && nan_cnt == 0 && stats_bad == 0);

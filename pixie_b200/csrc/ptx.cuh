@@ -124,6 +124,38 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint6
         : "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// Same, with the two descriptors given as (low word, shared high word): only the 14-bit start address in the low
+// word differs between operands / K steps, so the issuing thread needs one 32-bit add per operand per MMA.
+template <bool kAccumulate>
+__device__ __forceinline__ void umma_f16_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc) {
+    if (kAccumulate) {
+        asm volatile(
+            "{\n\t"
+            ".reg .b64 da, db;\n\t"
+            ".reg .pred p;\n\t"
+            "mov.b64 da, {%1, %3};\n\t"
+            "mov.b64 db, {%2, %3};\n\t"
+            "setp.eq.b32 p, 0, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t"
+            "}\n"
+            :
+            : "r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n\t"
+            ".reg .b64 da, db;\n\t"
+            ".reg .pred p;\n\t"
+            "mov.b64 da, {%1, %3};\n\t"
+            "mov.b64 db, {%2, %3};\n\t"
+            "setp.ne.b32 p, 0, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t"
+            "}\n"
+            :
+            : "r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc)
+            : "memory");
+    }
+}
 // Arrive on an mbarrier once all previously issued tcgen05.mma of this thread have retired.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
@@ -138,6 +170,14 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
           "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
           "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (r points at 32 consecutive array elements).
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32"
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_ld_wait() {

@@ -3,6 +3,8 @@ MPM_Simulator_WARP shim; oracle/mpm_ref.c is the checker (fp32 build = the refer
 fp64 build = drift reference). Tolerances: positions 1e-5 after 200 substeps against the fp32 oracle
 (measured ~1e-6; the GPU scatter order differs, so bit-exactness is not defined for float atomics —
 the reference itself is run-to-run non-deterministic, mpm_utils.py:393-394)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -13,8 +15,13 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
-def _pair(n, ng, materials, seed, prec="f32", bcs=True, g=(0.0, 0.0, -9.8), damping=0.9999, moving=True):
+def _pair(n, ng, materials, seed, prec="f32", bcs=True, g=(0.0, 0.0, -9.8), damping=0.9999, moving=True, tiled=False):
     from pixie_b200.mpm_solver_warp import MPM_Simulator_WARP
+    # the solver picks its path when the handle is created
+    if tiled:
+        os.environ["PIXIE_MPM_TILED"] = "1"
+    else:
+        os.environ.pop("PIXIE_MPM_TILED", None)
     sc = R.synthetic_scene(n, ng, seed=seed, materials=materials)
     s = MPM_Simulator_WARP(10)
     s.load_initial_data_from_torch(torch.from_numpy(sc["x"]).to(DEV), torch.from_numpy(sc["vol"]).to(DEV), None, n_grid=ng, grid_lim=2.0)
@@ -62,9 +69,10 @@ def _err(s, o, fid):
     return np.abs(a - o.get(fid).reshape(s.n_particles, -1)).max()
 
 
+@pytest.mark.parametrize("tiled", [False, True], ids=["three_kernel", "tiled"])
 @pytest.mark.parametrize("materials", [(0,), (2,), (1,), (5,), (3,), (0, 1, 2, 3, 4, 5, 6)])
-def test_rollout_matches_fp32_oracle(built_lib, cuda_dev, materials):
-    s, o, _ = _pair(5000, 32, materials, seed=3)
+def test_rollout_matches_fp32_oracle(built_lib, cuda_dev, materials, tiled):
+    s, o, _ = _pair(5000, 32, materials, seed=3, tiled=tiled)
     s.p2g2p(0, 1e-4); o.step(1, 1e-4)
     assert _err(s, o, "X") < 1e-7 and _err(s, o, "V") < 1e-5
     s.p2g2p_n(199, 1e-4); o.step(199, 1e-4)
@@ -137,10 +145,11 @@ def test_conservation_at_full_size(built_lib, cuda_dev):
     assert np.isfinite(x).all() and x.min() > 0.5 and x.max() < 1.5
 
 
-def test_drift_vs_fp64_oracle(built_lib, cuda_dev):
+@pytest.mark.parametrize("tiled", [False, True], ids=["three_kernel", "tiled"])
+def test_drift_vs_fp64_oracle(built_lib, cuda_dev, tiled):
     """Position drift against the fp64 oracle over a rollout, next to the fp32-oracle noise floor."""
     # (no moving collider here: the step at which its faces cross a node is precision dependent by design)
-    s, o64, _ = _pair(20_000, 48, (0,), seed=1, prec="f64", moving=False)
+    s, o64, _ = _pair(20_000, 48, (0,), seed=1, prec="f64", moving=False, tiled=tiled)
     _, o32, _ = _pair(20_000, 48, (0,), seed=1, prec="f32", moving=False)
     s.p2g2p_n(300, 1e-4); o64.step(300, 1e-4); o32.step(300, 1e-4)
     torch.cuda.synchronize()
