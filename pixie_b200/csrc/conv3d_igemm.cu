@@ -26,6 +26,11 @@ struct SmemCtrl {
     int abort_flag;
 };
 
+// bring-up event log: role r appends (clock64 << 8 | code) to trace[r * 4096 + n]
+#define PIXIE_TR(tr_, role_, n_, code_) do { if ((tr_) && (n_) < 4096) { (tr_)[(role_) * 4096 + (n_)] = (clock64() << 8) | (long long)(code_); ++(n_); } } while (0)
+
+constexpr int kPhasesSmemMax = 256;       // phase table copied to shared memory when it fits (4 KB)
+constexpr int kCtlBarrierBytes = 512;     // SmemCtrl
 constexpr int kStatsMaxC = 256;
 // per epilogue warp: [2][kStatsMaxC] floats (sum, sum of squares), private to the warp -> no atomics
 constexpr int kStatsSmemBytes = 4 * 2 * kStatsMaxC * 4;
@@ -53,7 +58,7 @@ struct TileCoord {
     int nb, d0, h0, w0, n0, ph_begin, ph_end, split, tde;
 };
 
-__device__ __forceinline__ TileCoord decode_tile(const ConvKernelParams& p, int wi) {
+__device__ __forceinline__ TileCoord decode_tile(const ConvKernelParams& p, int wi, int block_n, int TW, int TD) {
     TileCoord t;
     t.split = wi % p.split_k;
     int rest = wi / p.split_k;
@@ -65,13 +70,13 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvKernelParams& p, int 
     m /= p.tiles_h;
     int td = m % p.tiles_d;
     t.nb = m / p.tiles_d;
-    t.d0 = td * p.TD;
-    t.h0 = th * p.TH;
-    t.w0 = tw * p.TW;
-    t.n0 = nt * p.block_n;
+    t.d0 = td * TD;
+    t.h0 = th * (128 / TW);
+    t.w0 = tw * TW;
+    t.n0 = nt * block_n;
     t.ph_begin = (int)(((long long)t.split * p.n_phases) / p.split_k);
     t.ph_end = (int)(((long long)(t.split + 1) * p.n_phases) / p.split_k);
-    t.tde = min(p.TD, p.D - t.d0);
+    t.tde = min(TD, p.D - t.d0);
     return t;
 }
 
@@ -83,7 +88,7 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvKernelParams& p, int 
 // (r01: 240 instructions per slab at ~7 cycles each vs 12 x 96 tensor-pipe cycles).
 template <int BN, int TWv>
 __device__ __forceinline__ void issue_slab_3x3(uint32_t acc0, uint32_t a_lo0, uint32_t b_lo0, uint32_t hi, uint32_t idA,
-                                               uint32_t id_old, uint32_t id1, int nold, bool fresh) {
+                                               uint32_t id_old, uint32_t id1, int nold, bool fresh, bool only_first) {
     constexpr uint32_t kKh = (uint32_t)(TWv * 128) >> 4, kTap = (uint32_t)(BN * 128) >> 4;
     if (fresh) {
         // the newest plane's accumulator is overwritten by its first MMA, the older planes accumulate
@@ -92,6 +97,7 @@ __device__ __forceinline__ void issue_slab_3x3(uint32_t acc0, uint32_t a_lo0, ui
     } else {
         umma_f16_lohi<true>(acc0, a_lo0, b_lo0, hi, idA);
     }
+    if (only_first) return;      // bring-up timing experiment (debug_flags bit 2)
 #pragma unroll
     for (int i = 1; i < 12; ++i) {
         const uint32_t kh = (uint32_t)(i >> 2), k4 = (uint32_t)(i & 3);
@@ -99,8 +105,65 @@ __device__ __forceinline__ void issue_slab_3x3(uint32_t acc0, uint32_t a_lo0, ui
     }
 }
 
+// A whole 3x3x3 stride-1 phase of a full-depth tile (TDv output planes, TDv + 2 input slabs), issued by ONE elected thread
+// with the plane loop unrolled: which accumulators / weight blocks a slab feeds is a compile-time fact, so a slab costs the
+// issuing thread its barrier wait, ~5 uniform-datapath instructions per MMA and a commit. The per-slab bookkeeping of the
+// generic loop (~150 instructions, ~800 cycles on one warp) was the kernel's critical path (r01 timing experiments).
+// Returns false if a barrier timed out. `ss`/`sph` (slab ring position) are advanced identically in every lane.
+template <int BN, int TWv, int TDv>
+__device__ __forceinline__ bool mma_phase_3x3(SmemCtrl* ctl, int s_stages, uint32_t s_stage_bytes, int& ss, int& sph, uint32_t s_base0,
+                                              uint32_t w16, uint32_t acc_set, bool first_phase, uint32_t desc_lo, uint32_t desc_hi,
+                                              bool only_first, volatile int* abort_flag, long long* trace, int& ntr) {
+    constexpr uint32_t kTap = (uint32_t)(BN * 128) >> 4;
+    constexpr uint32_t id1 = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | (8u << 24);
+    constexpr uint32_t id2 = (1u << 4) | ((uint32_t)((2 * BN) >> 3) << 17) | (8u << 24);
+    constexpr uint32_t id3 = (1u << 4) | ((uint32_t)((3 * BN) >> 3) << 17) | (8u << 24);
+    bool ok = true;
+    const bool leader = elect_one();
+    if (leader) {
+        int s = ss, sp = sph;
+#pragma unroll
+        for (int pl = 0; pl < TDv + 2; ++pl) {
+            const int d_min = pl - 2 > 0 ? pl - 2 : 0, d_max = pl < TDv - 1 ? pl : TDv - 1;
+            const int nblk = d_max - d_min + 1, kd_hi = pl - d_min, nold = nblk - 1;
+            const uint32_t idA = nblk == 1 ? id1 : (nblk == 2 ? id2 : id3);
+            const uint32_t id_old = nold == 1 ? id1 : id2;
+            if (ok) {
+                PIXIE_TR(trace, 1, ntr, 3);
+                ok = mbar_wait(&ctl->sfull[s], (uint32_t)sp, abort_flag);
+                if (ok) {
+                    PIXIE_TR(trace, 1, ntr, 4);
+                    tc_fence_after();
+                    const uint32_t s16 = (s_base0 + (uint32_t)s * s_stage_bytes) >> 4;
+                    issue_slab_3x3<BN, TWv>(acc_set + (uint32_t)(d_min * BN), desc_lo | (s16 & 0x3FFFu),
+                                            desc_lo | ((w16 + (uint32_t)(2 - kd_hi) * kTap) & 0x3FFFu), desc_hi, idA, id_old, id1,
+                                            nold, first_phase && d_max == pl, only_first);
+                    umma_commit(&ctl->sempty[s]);        // slab slot free once these MMAs retire
+                    PIXIE_TR(trace, 1, ntr, 5);
+                    if (++s == s_stages) { s = 0; sp ^= 1; }
+                }
+            }
+        }
+    }
+    PIXIE_TR(leader ? trace : nullptr, 1, ntr, 15);      // (elect.sync picks lane 0 of a converged warp: same lane as the caller's log)
+    __syncwarp();
+    ok = (*abort_flag == 0);            // a timed-out wait in the elected lane raised the CTA-wide flag
+    PIXIE_TR(leader ? trace : nullptr, 1, ntr, 16);
+    int s = ss + TDv + 2;
+    while (s >= s_stages) { s -= s_stages; sph ^= 1; }
+    ss = s;
+    return ok;
+}
+
+// kBN / kTW / kTD = 0: generic kernel (everything read from the parameters). Non-zero: specialised for that tile shape --
+// loop bounds become constants and the MMA role contains ONE unrolled 3x3x3 phase issuer instead of a dispatch over twelve
+// (the all-in-one kernel was 240 KB of SASS with a 86 % instruction-cache hit rate; r01 profile).
+template <int kBN, int kTW, int kTD>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv3d_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
+    const int block_n = kBN ? kBN : p.block_n;
+    const int TW = kTW ? kTW : p.TW;
+    const int TD = kTD ? kTD : p.TD;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // dynamic smem base is only guaranteed 16 B aligned by the ABI: align manually to 1024 B
     uint8_t* smem = reinterpret_cast<uint8_t*>(
@@ -108,12 +171,19 @@ conv3d_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
     uint8_t* w_smem = smem;
     uint8_t* s_smem = smem + (size_t)p.w_stages * p.w_stage_bytes;
     SmemCtrl* ctl = reinterpret_cast<SmemCtrl*>(s_smem + (size_t)p.s_stages * p.s_stage_bytes);
-    float* stats_sm = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ctl) + 512);   // used iff p.stats
+    ConvPhase* phases_sm = reinterpret_cast<ConvPhase*>(reinterpret_cast<uint8_t*>(ctl) + kCtlBarrierBytes);
+    float* stats_sm = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(phases_sm) + kPhasesSmemMax * sizeof(ConvPhase));   // used iff p.stats
+    // The producer and the MMA issuer read one descriptor per phase on their critical path: from shared memory that is
+    // ~30 cycles, from global ~800 (a phase is only TD+2 slabs long).
+    const bool phases_in_smem = p.n_phases <= kPhasesSmemMax;
+    if (phases_in_smem)
+        for (int i = threadIdx.x; i < p.n_phases; i += blockDim.x) phases_sm[i] = p.phases[i];
+    const ConvPhase* phases = phases_in_smem ? phases_sm : p.phases;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int total_items = p.NB * p.tiles_d * p.tiles_h * p.tiles_w * p.n_tiles * p.split_k;
-    const uint32_t tmem_cols_needed = (uint32_t)(p.acc_sets * p.TD * p.block_n);
+    const uint32_t tmem_cols_needed = (uint32_t)(p.acc_sets * TD * block_n);
     uint32_t tmem_cols = 32;
     while (tmem_cols < tmem_cols_needed) tmem_cols <<= 1;
 
@@ -142,20 +212,23 @@ conv3d_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
         // ================================================================ TMA producer (warp-uniform, one elected lane issues)
         int ws = 0, wph = 0, ss = 0, sph = 0;
         int wcount = 0, scount = 0;     // bring-up only (debug_flags bit 1: stop re-loading once every stage was filled)
+        long long* tr = (blockIdx.x == 0 && lane == 0) ? p.trace : nullptr; int ntr = 0;
         bool ok = true;
         for (int wi = blockIdx.x; wi < total_items && ok; wi += gridDim.x) {
-            const TileCoord t = decode_tile(p, wi);
+            const TileCoord t = decode_tile(p, wi, block_n, TW, TD);
             for (int ph = t.ph_begin; ph < t.ph_end && ok; ++ph) {
-                const ConvPhase P = p.phases[ph];
+                const ConvPhase P = phases[ph];
                 const int ntaps = P.n_kh * P.n_kd;
+                PIXIE_TR(tr, 0, ntr, 1);
                 ok = mbar_wait(&ctl->wempty[ws], wph ^ 1, abort_flag);
                 if (!ok) break;
+                PIXIE_TR(tr, 0, ntr, 2);
                 if ((p.debug_flags & 2) && wcount >= p.w_stages) { if (elect_one()) mbar_arrive(&ctl->wfull[ws]); }
                 else if (elect_one()) {
-                    mbar_expect_tx(&ctl->wfull[ws], (uint32_t)(ntaps * p.block_n * 128));
+                    mbar_expect_tx(&ctl->wfull[ws], (uint32_t)(ntaps * block_n * 128));
                     uint8_t* wdst = w_smem + (size_t)ws * p.w_stage_bytes;
                     for (int tap = 0; tap < ntaps; ++tap)
-                        tma_load_2d(wdst + (size_t)tap * p.block_n * 128, &p.tmB, &ctl->wfull[ws],
+                        tma_load_2d(wdst + (size_t)tap * block_n * 128, &p.tmB, &ctl->wfull[ws],
                                     (P.wtile_base + tap) * 64, t.n0);
                 }
                 ++wcount;
@@ -164,8 +237,10 @@ conv3d_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
                 const int nplanes = t.tde + P.n_kd - 1;
                 const uint32_t slab_bytes = (uint32_t)p.slab_rows[P.src] * 128u;
                 for (int pl = 0; pl < nplanes && ok; ++pl) {
+                    PIXIE_TR(tr, 0, ntr, 3);
                     ok = mbar_wait(&ctl->sempty[ss], sph ^ 1, abort_flag);
                     if (!ok) break;
+                    PIXIE_TR(tr, 0, ntr, 4);
                     if ((p.debug_flags & 2) && scount >= p.s_stages) { if (elect_one()) mbar_arrive(&ctl->sfull[ss]); }
                     else if (elect_one()) {
                         mbar_expect_tx(&ctl->sfull[ss], slab_bytes);
@@ -174,6 +249,7 @@ conv3d_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
                                     t.h0 * p.stride + P.dh0, (t.d0 + pl) * p.stride + P.dd0, t.nb);
                     }
                     ++scount;
+                    PIXIE_TR(tr, 0, ntr, 5);
                     if (++ss == p.s_stages) { ss = 0; sph ^= 1; }
                 }
             }
@@ -185,28 +261,41 @@ conv3d_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
         // elected lane. A single divergent thread costs ~25 scalar instructions per MMA (ncu: tensor pipe
         // 23 % busy, issue thread never waiting).
         int ws = 0, wph = 0, ss = 0, sph = 0, as = 0, aph = 0;
-        const int max_blk = min(3, 256 / p.block_n);                             // accumulator blocks one MMA may span
-        const uint32_t idesc1 = make_idesc_f16(128, (uint32_t)p.block_n), idesc2 = make_idesc_f16(128, (uint32_t)(2 * p.block_n)),
-                       idesc3 = make_idesc_f16(128, (uint32_t)(3 * p.block_n));
+        long long* mtr = (blockIdx.x == 0) ? p.trace : nullptr; int mntr = 0;
+        const int max_blk = min(3, 256 / block_n);                             // accumulator blocks one MMA may span
+        const uint32_t idesc1 = make_idesc_f16(128, (uint32_t)block_n), idesc2 = make_idesc_f16(128, (uint32_t)(2 * block_n)),
+                       idesc3 = make_idesc_f16(128, (uint32_t)(3 * block_n));
         const uint64_t desc_fixed = (make_sw128_desc(0, 1024) ^ p.desc_xor);   // everything but the start address
         const uint32_t desc_lo = (uint32_t)desc_fixed, desc_hi = (uint32_t)(desc_fixed >> 32);
-        const bool fast3 = (p.block_n == 64 || p.block_n == 128) && (p.TW == 16 || p.TW == 8);
         const uint32_t w_base0 = smem_u32(w_smem), s_base0 = smem_u32(s_smem);
-        const uint32_t kh_stride16 = (uint32_t)(p.TW * 128) >> 4;             // descriptor units of 16 B
-        const uint32_t tap_stride16 = (uint32_t)(p.block_n * 128) >> 4;
+        const uint32_t kh_stride16 = (uint32_t)(TW * 128) >> 4;             // descriptor units of 16 B
+        const uint32_t tap_stride16 = (uint32_t)(block_n * 128) >> 4;
         bool ok = true;
         for (int wi = blockIdx.x; wi < total_items && ok; wi += gridDim.x) {
-            const TileCoord t = decode_tile(p, wi);
+            if (lane == 0) PIXIE_TR(mtr, 1, mntr, 14);
+            const TileCoord t = decode_tile(p, wi, block_n, TW, TD);
+            if (lane == 0) PIXIE_TR(mtr, 1, mntr, 6);
             ok = mbar_wait(&ctl->tempty[as], aph ^ 1, abort_flag);
             if (!ok) break;
+            if (lane == 0) PIXIE_TR(mtr, 1, mntr, 7);
             tc_fence_after();
             for (int ph = t.ph_begin; ph < t.ph_end && ok; ++ph) {
-                const ConvPhase P = p.phases[ph];
+                const ConvPhase P = phases[ph];
                 const int n_kd = P.n_kd, n_kh = P.n_kh;
+                if (lane == 0) PIXIE_TR(mtr, 1, mntr, 1);
                 ok = mbar_wait(&ctl->wfull[ws], wph, abort_flag);
                 if (!ok) break;
+                if (lane == 0) PIXIE_TR(mtr, 1, mntr, 2);
                 const uint32_t w16 = (w_base0 + (uint32_t)(ws * p.w_stage_bytes)) >> 4;
                 const int nplanes = t.tde + n_kd - 1;
+                if (kBN != 0 && n_kh == 3 && n_kd == 3 && t.tde == TD) {
+                    const uint32_t acc_set = tmem_base + (uint32_t)(as * TD * block_n);
+                    const bool first = (ph == t.ph_begin), of = (p.debug_flags & 4) != 0;
+                    if constexpr (kBN != 0)
+                        ok = mma_phase_3x3<kBN ? kBN : 64, kTW ? kTW : 16, kTD ? kTD : 1>(ctl, p.s_stages, (uint32_t)p.s_stage_bytes, ss, sph, s_base0, w16,
+                                                                                  acc_set, first, desc_lo, desc_hi, of, abort_flag, mtr, mntr);
+                    if (lane == 0) PIXIE_TR(mtr, 1, mntr, 11);
+                } else
                 for (int pl = 0; pl < nplanes && ok; ++pl) {
                     ok = mbar_wait(&ctl->sfull[ss], sph, abort_flag);
                     if (!ok) break;
@@ -220,23 +309,9 @@ conv3d_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
                     const int nblk = d_max - d_min + 1, kd_hi = pl - d_min;
                     const bool fresh = (ph == t.ph_begin) && (d_max == pl);   // plane pl's accumulator is first touched here
                     if (elect_one()) {
-                        const uint32_t acc0 = tmem_base + (uint32_t)((as * p.TD + d_min) * p.block_n);
+                        const uint32_t acc0 = tmem_base + (uint32_t)((as * TD + d_min) * block_n);
                         const uint32_t wblk0 = (uint32_t)(n_kd - 1 - kd_hi);
                         const int nold0 = fresh ? nblk - 1 : nblk;
-                        if (n_kh == 3 && n_kd == 3 && nblk <= max_blk && fast3) {
-                            const uint32_t idA = nblk == 1 ? idesc1 : (nblk == 2 ? idesc2 : idesc3);
-                            const int nold = nblk - 1;
-                            const uint32_t id_old = nold == 1 ? idesc1 : idesc2;
-                            const uint32_t a_lo0 = desc_lo | (s16 & 0x3FFFu);
-                            const uint32_t b_lo0 = desc_lo | ((w16 + wblk0 * tap_stride16) & 0x3FFFu);
-                            if (p.block_n == 64) {
-                                if (p.TW == 16) issue_slab_3x3<64, 16>(acc0, a_lo0, b_lo0, desc_hi, idA, id_old, idesc1, nold, fresh);
-                                else issue_slab_3x3<64, 8>(acc0, a_lo0, b_lo0, desc_hi, idA, id_old, idesc1, nold, fresh);
-                            } else {
-                                if (p.TW == 16) issue_slab_3x3<128, 16>(acc0, a_lo0, b_lo0, desc_hi, idA, id_old, idesc1, nold, fresh);
-                                else issue_slab_3x3<128, 8>(acc0, a_lo0, b_lo0, desc_hi, idA, id_old, idesc1, nold, fresh);
-                            }
-                        } else
                         for (int kh = 0; kh < n_kh; ++kh) {
                             const uint32_t a16 = s16 + (uint32_t)kh * kh_stride16;
                             const uint32_t b16 = w16 + ((uint32_t)kh * (uint32_t)n_kd + wblk0) * tap_stride16;
@@ -249,11 +324,11 @@ conv3d_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
                                     const int cnt = min(max_blk, nold - b);
                                     const uint32_t idn = (cnt == 1) ? idesc1 : (cnt == 2 ? idesc2 : idesc3);
                                     const uint64_t db = desc_fixed | (uint64_t)((b16 + (uint32_t)b * tap_stride16 + 2u * k4) & 0x3FFFu);
-                                    umma_f16(acc0 + (uint32_t)(b * p.block_n), da, db, idn, 1u);
+                                    umma_f16(acc0 + (uint32_t)(b * block_n), da, db, idn, 1u);
                                 }
                                 if (split_new) {
                                     const uint64_t db = desc_fixed | (uint64_t)((b16 + (uint32_t)(nblk - 1) * tap_stride16 + 2u * k4) & 0x3FFFu);
-                                    umma_f16(acc0 + (uint32_t)((nblk - 1) * p.block_n), da, db, idesc1, 0u);
+                                    umma_f16(acc0 + (uint32_t)((nblk - 1) * block_n), da, db, idesc1, 0u);
                                 }
                             }
                         }
@@ -262,9 +337,11 @@ conv3d_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
                     if (++ss == p.s_stages) { ss = 0; sph ^= 1; }
                 }
                 if (elect_one()) umma_commit(&ctl->wempty[ws]);
+                if (lane == 0) PIXIE_TR(mtr, 1, mntr, 12);
                 if (++ws == p.w_stages) { ws = 0; wph ^= 1; }
             }
             if (elect_one()) umma_commit(&ctl->tfull[as]);            // accumulators complete
+            if (lane == 0) PIXIE_TR(mtr, 1, mntr, 13);
             __syncwarp();
             if (++as == p.acc_sets) { as = 0; aph ^= 1; }
         }
@@ -272,7 +349,7 @@ conv3d_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
         // ================================================================ epilogue (warps 2..5)
         const int q = warp & 3;                 // TMEM lane quarter this warp may access
         const int r = q * 32 + lane;            // accumulator row = voxel inside the plane tile
-        const int th = r / p.TW, tw = r % p.TW;
+        const int th = r / TW, tw = r % TW;
         int as = 0, aph = 0;
         bool ok = true;
         const long long DHW = (long long)p.D * p.H * p.W;
@@ -338,11 +415,14 @@ conv3d_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
             }
             __syncwarp();
         };
+        long long* etr = (blockIdx.x == 0 && warp == 2 && lane == 0) ? p.trace : nullptr; int entr = 0;
         const bool wide_ok = !p.out_planar && ((p.out_ld & 3) == 0) && ((p.out_c0 & 3) == 0);
         for (int wi = blockIdx.x; wi < total_items && ok; wi += gridDim.x) {
-            const TileCoord t = decode_tile(p, wi);
+            const TileCoord t = decode_tile(p, wi, block_n, TW, TD);
+            PIXIE_TR(etr, 2, entr, 8);
             ok = mbar_wait(&ctl->tfull[as], aph, abort_flag);
             if (!ok) break;
+            PIXIE_TR(etr, 2, entr, 9);
             tc_fence_after();
             if (do_stats && stats_nb != t.nb) {
                 if (stats_nb >= 0) flush_stats(stats_nb);
@@ -354,11 +434,11 @@ conv3d_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
             for (int d = 0; d < t.tde && !(p.debug_flags & 1); ++d) {
                 const long long vox = ((long long)(t.d0 + d) * p.H + hh) * p.W + ww;   // inside batch item
                 const uint32_t acc = tmem_base + ((uint32_t)(q * 32) << 16) +
-                                     (uint32_t)((as * p.TD + d) * p.block_n);
+                                     (uint32_t)((as * TD + d) * block_n);
                 int c = 0;
                 // ---- wide path: 64 channels per step. One warp per scheduler means nothing hides latency but the
                 // warp's own ILP: both TMEM loads and all 16 residual loads are in flight before the first use.
-                for (; wide_ok && c + 64 <= p.block_n && t.n0 + c + 64 <= p.Cout; c += 64) {
+                for (; wide_ok && c + 64 <= block_n && t.n0 + c + 64 <= p.Cout; c += 64) {
                     const int ch0 = t.n0 + c;
                     uint32_t v[64];
                     tmem_ld32(acc + (uint32_t)c, v);
@@ -426,7 +506,7 @@ conv3d_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
                     }
                 }
                 // ---- generic path: 16 channels per step (ragged Cout, planar outputs, narrow tiles)
-                for (; c < p.block_n; c += 16) {
+                for (; c < block_n; c += 16) {
                     uint32_t v[16];
                     tmem_ld16(acc + (uint32_t)c, v);
                     tmem_ld_wait();
@@ -502,6 +582,7 @@ conv3d_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
             }
             tc_fence_before();
             __syncwarp();
+            PIXIE_TR(etr, 2, entr, 10);
             if (lane == 0) mbar_arrive(&ctl->tempty[as]);
             if (++as == p.acc_sets) { as = 0; aph ^= 1; }
         }
@@ -515,6 +596,29 @@ conv3d_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
         tc_fence_after();
         tmem_dealloc(tmem_base, tmem_cols);
     }
+}
+
+// Kernel variants: index 0 is the generic kernel, 1.. the (block_n, TW, TD) specialisations of the 3x3x3 fast path.
+using ConvKernelFn = void (*)(const ConvKernelParams);
+#define PIXIE_CONV_VARIANTS(X) \
+    X(64, 16, 1) X(64, 16, 2) X(64, 16, 3) X(64, 16, 4) X(64, 8, 1) X(64, 8, 2) X(64, 8, 3) X(64, 8, 4) \
+    X(128, 16, 1) X(128, 16, 2) X(128, 8, 1) X(128, 8, 2)
+constexpr int kNumConvVariants = 13;
+static ConvKernelFn conv_variant_kernel(int v) {
+    static const ConvKernelFn tab[kNumConvVariants] = {
+        conv3d_igemm_kernel<0, 0, 0>,
+#define X(bn, tw, td) conv3d_igemm_kernel<bn, tw, td>,
+        PIXIE_CONV_VARIANTS(X)
+#undef X
+    };
+    return tab[v];
+}
+static int conv_variant_index(int block_n, int TW, int TD) {
+    int i = 1;
+#define X(bn, tw, td) if (block_n == bn && TW == tw && TD == td) return i; ++i;
+    PIXIE_CONV_VARIANTS(X)
+#undef X
+    return 0;
 }
 
 // =====================================================================================  host side
@@ -687,6 +791,7 @@ int conv_plan_create(const ConvDesc& d, int* d_err_flag, ConvPlan& plan, char* e
     memset(&p, 0, sizeof(p));
     p.NB = d.NB; p.D = d.D; p.H = d.H; p.W = d.W; p.stride = d.stride;
     p.TW = (d.W >= 16) ? 16 : 8;
+    if (const char* e = getenv("PIXIE_CONV_TW")) p.TW = atoi(e);      // bring-up override
     p.TH = 128 / p.TW;
     p.Cout = d.Cout;
 
@@ -707,9 +812,11 @@ int conv_plan_create(const ConvDesc& d, int* d_err_flag, ConvPlan& plan, char* e
 
     // TD: accumulators per set
     int td = d.td ? d.td : std::min(4, 512 / (2 * bn));
+    int td_forced = d.td;
+    if (const char* e = getenv("PIXIE_CONV_TD")) { td = atoi(e); td_forced = td; }   // bring-up override
     td = std::max(1, std::min(td, d.D));
     if (!any3) td = std::min(td, 2);    // no plane re-use without kd taps: smaller tiles, more CTAs
-    if (!d.td && td > 1) {
+    if (!td_forced && td > 1) {
         // wave quantisation: a persistent grid of `sms` CTAs finishes in ceil(tiles/sms) rounds; prefer the
         // plane count with the better last-round fill (64^3: TD=4 -> 512 tiles = 3.46 rounds, TD=2 -> 6.92)
         int dev = 0, sms = 148;
@@ -748,13 +855,14 @@ int conv_plan_create(const ConvDesc& d, int* d_err_flag, ConvPlan& plan, char* e
     for (size_t i = 0; i < slots.size(); ++i) max_rows = std::max(max_rows, p.slab_rows[i]);
     p.w_stage_bytes = max_taps * bn * 128;
     p.s_stage_bytes = max_rows * 128;
-    const int avail = 227 * 1024 - 2048;   // 1 KB alignment slack + control block
+    const int avail = 227 * 1024 - (1024 + kCtlBarrierBytes + kPhasesSmemMax * (int)sizeof(ConvPhase));   // alignment slack + control block
     p.w_stages = (2 * p.w_stage_bytes + 2 * p.s_stage_bytes <= avail) ? 2 : 1;
     if (p.w_stages * p.w_stage_bytes + 2 * p.s_stage_bytes > avail) return fail("tile does not fit in shared memory");
     p.s_stages = std::min(kMaxSStages, (avail - p.w_stages * p.w_stage_bytes) / p.s_stage_bytes);
     p.s_stages = std::min(p.s_stages, 6);
     plan.fused_stats = d.stats != nullptr && split == 1 && d.Cout <= kStatsMaxC && !d.out_planar;
-    const int ctl_bytes = 2048 + (plan.fused_stats ? kStatsSmemBytes : 0);
+    // 1 KB slack for the manual 1024 B alignment of the dynamic smem base + barriers + phase table (+ statistics scratch)
+    const int ctl_bytes = 1024 + kCtlBarrierBytes + kPhasesSmemMax * (int)sizeof(ConvPhase) + (plan.fused_stats ? kStatsSmemBytes : 0);
     {
         const int avail2 = 227 * 1024 - ctl_bytes;
         while (p.s_stages > 2 && p.w_stages * p.w_stage_bytes + p.s_stages * p.s_stage_bytes > avail2) --p.s_stages;
@@ -789,6 +897,7 @@ int conv_plan_create(const ConvDesc& d, int* d_err_flag, ConvPlan& plan, char* e
     p.stats_scalar = d.stats_scalar ? 1 : 0;
     p.desc_xor = 0;
     p.debug_flags = 0;
+    p.trace = nullptr;
     plan.out_bytes = d.out_planar ? (size_t)d.NB * d.Cout * d.D * d.H * d.W * 4
                                   : (size_t)d.NB * d.D * d.H * d.W * p.out_ld * 4;
 
@@ -797,10 +906,12 @@ int conv_plan_create(const ConvDesc& d, int* d_err_flag, ConvPlan& plan, char* e
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     plan.grid = std::min(items * split, sms);
 
+    plan.variant = conv_variant_index(p.block_n, p.TW, p.TD);
     static bool attr_set = false;
     if (!attr_set) {
-        if (cudaFuncSetAttribute(conv3d_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
-            return fail("cudaFuncSetAttribute(max dynamic smem)");
+        for (int v = 0; v < kNumConvVariants; ++v)
+            if (cudaFuncSetAttribute(conv_variant_kernel(v), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+                return fail("cudaFuncSetAttribute(max dynamic smem)");
         attr_set = true;
     }
     return 0;
@@ -817,7 +928,7 @@ int conv_plan_launch(const ConvPlan& plan, cudaStream_t stream) {
         // cleared when out_ld > Cout, so callers with sliced outputs must not use split-K.
         cudaMemsetAsync(plan.p.out, 0, plan.out_bytes, stream);
     }
-    conv3d_igemm_kernel<<<plan.grid, kConvThreads, plan.smem_bytes, stream>>>(plan.p);
+    conv_variant_kernel(plan.variant)<<<plan.grid, kConvThreads, plan.smem_bytes, stream>>>(plan.p);
     return (int)cudaGetLastError();
 }
 

@@ -144,6 +144,12 @@ int main(int argc, char** argv) {
         }
         plan.p.desc_xor = hi_xor;
         if (getenv("CONV_DEBUG")) plan.p.debug_flags = atoi(getenv("CONV_DEBUG"));
+        long long* d_trace = nullptr;
+        if (getenv("CONV_TRACE") && c.timing) {
+            CK(cudaMalloc(&d_trace, 4 * 4096 * sizeof(long long)));
+            CK(cudaMemset(d_trace, 0, 4 * 4096 * sizeof(long long)));
+            plan.p.trace = d_trace;
+        }
         printf("[%s] grid=%d smem=%d bn=%d TD=%d TW=%d TH=%d acc_sets=%d w_stages=%d s_stages=%d phases=%d split=%d\n",
                c.name.c_str(), plan.grid, plan.smem_bytes, plan.p.block_n, plan.p.TD, plan.p.TW, plan.p.TH,
                plan.p.acc_sets, plan.p.w_stages, plan.p.s_stages, plan.p.n_phases, plan.p.split_k);
@@ -161,6 +167,22 @@ int main(int argc, char** argv) {
             continue;
         }
 
+        if (d_trace) {
+            // one traced launch: dump CTA 0's event log (role, code, cycle relative to the first event)
+            conv_plan_launch(plan, 0);
+            CK(cudaDeviceSynchronize());
+            std::vector<long long> h_tr(4 * 4096);
+            CK(cudaMemcpy(h_tr.data(), d_trace, h_tr.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+            long long t0 = -1;
+            for (long long v : h_tr) if (v && (t0 < 0 || (v >> 8) < t0)) t0 = v >> 8;
+            FILE* f = fopen(getenv("CONV_TRACE"), "w");
+            for (int r = 0; r < 4; ++r)
+                for (int i = 0; i < 4096 && h_tr[r * 4096 + i]; ++i)
+                    fprintf(f, "%d %d %lld\n", r, (int)(h_tr[r * 4096 + i] & 0xFF), (h_tr[r * 4096 + i] >> 8) - t0);
+            fclose(f);
+            plan.p.trace = nullptr;
+            cudaFree(d_trace);
+        }
         if (c.timing) {
             cudaEvent_t e0, e1;
             cudaEventCreate(&e0); cudaEventCreate(&e1);

@@ -44,7 +44,18 @@ __global__ void __launch_bounds__(128, 1) mma_bench_kernel(int N, int iters, int
         t0 = clock64();
         if (elect_one()) {
             int acc = 0, inrun = 0;
-            if (mode == 4) {
+            if (mode == 5) {
+                // latency: `run` MMAs, commit, wait for the mbarrier, repeat (issue -> retire -> visible to the issuing thread)
+                const uint32_t lo = (uint32_t)dfix, hi = (uint32_t)(dfix >> 32);
+                uint32_t par = 1;
+                for (int i = 0; i < iters; i += run) {
+                    for (int k = 0; k < run; ++k)
+                        umma_f16_lohi<true>(tmem_base, (lo | a16) + (uint32_t)((k & 3) * 2), (lo | b16) + (uint32_t)((k & 3) * 2), hi, idesc);
+                    umma_commit(&bar);
+                    while (!mbar_try_wait(&bar, par)) {}
+                    par ^= 1;
+                }
+            } else if (mode == 4) {
                 // fully unrolled: 12 MMAs per iteration, every operand offset an immediate (the conv kernel's issue pattern);
                 // the rolled loop below spends 50-70 cycles per iteration on its own index arithmetic and hides the pipe's rate
                 const uint32_t lo = (uint32_t)dfix, hi = (uint32_t)(dfix >> 32);
@@ -65,10 +76,10 @@ __global__ void __launch_bounds__(128, 1) mma_bench_kernel(int N, int iters, int
                 if (mode == 1) { acc = (acc + 1 == nacc) ? 0 : acc + 1; }
                 else if (mode >= 2) { if (++inrun == run) { inrun = 0; acc = (acc + 1 == nacc) ? 0 : acc + 1; } }
             }
-            umma_commit(&bar);
+            if (mode != 5) umma_commit(&bar);
         }
         __syncwarp();
-        while (!mbar_try_wait(&bar, 1)) {}
+        if (mode != 5) while (!mbar_try_wait(&bar, 1)) {}
         t1 = clock64();
         if (threadIdx.x == 32 && blockIdx.x == 0) out->cycles = t1 - t0;
     }
@@ -96,6 +107,8 @@ int main() {
         {64, 4, 1, 0, 0, "unrolled N=64  one acc", 1, 0, 0},   {64, 4, 4, 0, 0, "unrolled N=64  D +64 /12, 4 acc", 1, 0, 64},
         {128, 4, 1, 0, 0, "unrolled N=128 one acc", 1, 0, 0},  {128, 4, 3, 0, 0, "unrolled N=128 D +64 /12, 3 pos", 1, 0, 64},
         {192, 4, 1, 0, 0, "unrolled N=192 one acc", 1, 0, 0},  {192, 4, 2, 0, 0, "unrolled N=192 D +64 /12, 2 pos", 1, 0, 64},
+        {64, 5, 1, 1, 0, "latency: 1 x N=64 + commit + wait", 1, 0, 0},   {64, 5, 1, 12, 0, "latency: 12 x N=64 + commit + wait", 1, 0, 0},
+        {128, 5, 1, 1, 0, "latency: 1 x N=128 + commit + wait", 1, 0, 0}, {128, 5, 1, 12, 0, "latency: 12 x N=128 + commit + wait", 1, 0, 0},
         {256, 4, 1, 0, 0, "unrolled N=256 one acc", 1, 0, 0},  {256, 4, 2, 0, 0, "unrolled N=256 D +128 /12, 2 pos", 1, 0, 128},
     };
     for (const Cfg& c : cfgs) {

@@ -42,7 +42,6 @@ struct DevT {          // fp32 activation [NB][sp^3][C]
     float* p = nullptr;
     int C = 0, sp = 0;
     double* stats = nullptr;   // [NB][C][2] (sum, sumsq over voxels), filled by the producer when requested
-    ConvOp* producer = nullptr;   // conv whose epilogue fills `stats` (totals only, until a GroupNorm consumer asks for channels)
 };
 
 }  // namespace
@@ -152,10 +151,7 @@ struct Builder {
                    int act, const F16* dst, int c0, const F16* raw, int raw_c0) {
         NormArgs a;
         a.x = x.p; a.V = (int)vox(x.sp); a.C = x.C; a.stats = stats; a.mode = mode; a.groups = groups;
-        // fused statistics default to the two per-item totals (all a LayerNorm needs, and nearly free in the conv
-        // epilogue); a GroupNorm consumer switches its producer to per-channel sums. The launch lambda reads the
-        // plan at launch time, so flipping the flag after the conv was emitted is fine.
-        if (mode == kNormGN && groups > 1 && x.producer) x.producer->plan.p.stats_scalar = 0;
+
         a.gamma = gamma; a.beta = beta; a.eps = 1e-5f; a.act = act;
         if (dst) { a.dst = dst->hi; a.dst_lo = dst->lo; a.dst_ld = dst->C; a.dst_c0 = c0; }
         if (raw) { a.raw_dst = raw->hi; a.raw_lo = raw->lo; a.raw_ld = raw->C; a.raw_c0 = raw_c0; }
@@ -218,7 +214,7 @@ struct Builder {
         d.bias = upload(bias);
         d.residual = residual;
         d.out = out; d.out_ld = Cout; d.out_c0 = 0; d.out_planar = planar ? 1 : 0;
-        if (want_stats) { want_stats->stats = stats_slot(Cout); d.stats = want_stats->stats; d.stats_scalar = true; }
+        if (want_stats) { want_stats->stats = stats_slot(Cout); d.stats = want_stats->stats; }
         char e[256] = {0};
         if (conv_plan_create(d, u.d_err, op->plan, e, sizeof(e))) { fail(e); return nullptr; }
         ConvOp* raw = op.get();
@@ -233,7 +229,6 @@ struct Builder {
         });
         u.op_kinds.push_back(PIXIE_OP_CONV); u.op_flops.push_back(u.flops - flops_before);
         const bool fused = raw->plan.fused_stats;
-        if (want_stats) want_stats->producer = fused ? raw : nullptr;
         u.convs.push_back(std::move(op));
         if (want_stats && !fused) emit_moments(*want_stats, want_stats->stats);
         return raw;
