@@ -22,6 +22,8 @@
 #include <string>
 #include <vector>
 
+#include <cub/cub.cuh>
+
 namespace pixie {
 
 using namespace mpm;
@@ -45,6 +47,7 @@ struct DevState {
     float *x, *v, *F, *F_trial, *C, *stress, *R, *cov, *init_cov;
     float *vol, *mass, *density, *E, *nu, *mu, *lam, *bulk, *yield_stress;
     int *material, *selection;
+    const int* order;   // thread i of p2g handles particle order[i] (cell-sorted, possibly a few substeps stale), or nullptr
     // grid
     float4* grid_mv;    // {momentum.xyz, mass}
     float4* grid_v;     // {velocity.xyz, 0}
@@ -59,6 +62,7 @@ struct DevState {
     float gx, gy, gz;
     float rpic_damping, grid_v_damping_scale, alpha, hardening, xi, plastic_viscosity, softening;
     int update_cov_with_F;
+    int scatter_slices;       // 3: one thread per (particle, x-slice of the stencil); 1: one thread per particle
 };
 
 __device__ __forceinline__ M3 load_m3(const float* p, int i) {
@@ -97,10 +101,15 @@ __device__ __forceinline__ Weights bspline_t(float inv_dx, float px, float py, f
 __device__ __forceinline__ Weights bspline(const DevState& s, float px, float py, float pz) { return bspline_t(s.inv_dx, px, py, pz); }
 
 // ------------------------------------------------------------------------------------------ p2g
+// Substep part 1, one thread per particle: pre-p2g particle operations, return mapping, stress.
+// Writes v (if a BC changed it), F, stress (and yield_stress / mu / lam where a return map updates them).
+// The scatter itself is mpm_scatter_kernel: at 1e5 particles a single kernel that does both is one long dependent
+// instruction stream on ~20 warps per SM (r01 ncu: 4600 instructions per thread, issue slots 36 % used).
 __global__ void __launch_bounds__(128)
-mpm_p2g_kernel(const DevState s, const float dt) {
+mpm_stress_kernel(const DevState s, const float dt) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= s.n) return;
+    const bool live = true;
     const float time = (float)(*s.time);
     float vx = s.v[3 * p], vy = s.v[3 * p + 1], vz = s.v[3 * p + 2];
     const float px = s.x[3 * p], py = s.x[3 * p + 1], pz = s.x[3 * p + 2];
@@ -146,9 +155,10 @@ mpm_p2g_kernel(const DevState s, const float dt) {
             }
         }
     }
-    if (v_dirty) { s.v[3 * p] = vx; s.v[3 * p + 1] = vy; s.v[3 * p + 2] = vz; }
+    if (v_dirty && live) { s.v[3 * p] = vx; s.v[3 * p + 1] = vy; s.v[3 * p + 2] = vz; }
 
     if (s.selection[p] != 0) return;
+    const bool contrib = true;
 
     // ---- compute_stress_from_F_trial (mpm_utils.py:467-526)
     const int material = s.material[p];
@@ -159,7 +169,7 @@ mpm_p2g_kernel(const DevState s, const float dt) {
         float ys = s.yield_stress[p];
         const float ys0 = ys;
         F = return_von_mises(Ft, mu, lam, ys, s.hardening, s.xi, false, 0.f, mu, lam);
-        if (ys != ys0) s.yield_stress[p] = ys;
+        if (ys != ys0 && contrib) s.yield_stress[p] = ys;
     } else if (material == 2) {
         F = return_sand(Ft, mu, lam, s.alpha);
     } else if (material == 3) {
@@ -168,29 +178,49 @@ mpm_p2g_kernel(const DevState s, const float dt) {
         float ys = s.yield_stress[p];
         const float ys0 = ys, mu0 = mu;
         F = return_von_mises(Ft, mu, lam, ys, s.hardening, s.xi, true, s.softening, mu, lam);
-        if (ys != ys0) s.yield_stress[p] = ys;
-        if (mu != mu0) { s.mu[p] = mu; s.lam[p] = lam; }
+        if (ys != ys0 && contrib) s.yield_stress[p] = ys;
+        if (mu != mu0 && contrib) { s.mu[p] = mu; s.lam[p] = lam; }
     }
-    store_m3(s.F, p, F);
+    if (contrib) store_m3(s.F, p, F);
     const float J = m3_det(F);
     M3 tau = m3_zero();
     if (material == 6) {
         tau = stress_water(J, s.bulk[p]);
-    } else if (material != 4 && material >= 0 && material <= 5) {
+    } else if (material == 0 || material == 5) {
+        // fixed-corotated stress needs only R = U V^T: Newton polar iteration, SVD only if it does not converge
+        M3 R;
+        if (polar_rotation(F, R)) tau = stress_fcr_R(F, R, J, mu, lam);
+        else { M3 U, V; V3 sig; svd3(F, U, sig, V); tau = stress_fcr(F, U, V, J, mu, lam); }
+    } else if (material >= 1 && material <= 3) {
         M3 U, V; V3 sig;
         svd3(F, U, sig, V);
-        if (material == 0 || material == 5) tau = stress_fcr(F, U, V, J, mu, lam);
-        else if (material == 1 || material == 3) tau = stress_stvk(F, U, V, sig, mu, lam);
-        else if (material == 2) tau = stress_drucker_prager(F, U, V, sig, mu, lam);
+        if (material == 1 || material == 3) tau = stress_stvk(F, U, V, sig, mu, lam);
+        else tau = stress_drucker_prager(F, U, V, sig, mu, lam);
     }
     {   // enforce symmetry
         const M3 tt = m3_t(tau);
 #pragma unroll
         for (int i = 0; i < 9; ++i) tau.m[i] = (tau.m[i] + tt.m[i]) / 2.0f;
     }
-    store_m3(s.stress, p, tau);
+    if (contrib) store_m3(s.stress, p, tau);
+}
 
-    // ---- p2g_apic_with_stress (mpm_utils.py:338-394)
+// Substep part 2: scatter of slice i = blockIdx.y of the 3x3x3 stencil (9 nodes) with warp-aggregated atomics.
+// Threads walk the particles in cell order (`s.order`), so the lanes of a warp hold runs of particles with the SAME base
+// cell = the same target nodes; each run (chopped at 8 lanes) is summed with 3 segmented shuffle steps per value and only
+// the run's first lane issues the red.global.add.v4. Runs are found from the keys the lanes compute THIS substep, so a
+// stale order costs efficiency, never correctness. (mpm_utils.py:338-394)
+template <int kSlices>
+__global__ void __launch_bounds__(128)
+mpm_scatter_kernel(const DevState s, const float dt) {
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = tid < s.n;
+    const int p = live ? (s.order ? s.order[tid] : tid) : 0;
+    const bool contrib = live && s.selection[p] == 0;
+    const float vx = s.v[3 * p], vy = s.v[3 * p + 1], vz = s.v[3 * p + 2];
+    const float px = s.x[3 * p], py = s.x[3 * p + 1], pz = s.x[3 * p + 2];
+    const float mass = s.mass[p];
+    const M3 tau = load_m3(s.stress, p);
     const Weights W = bspline(s, px, py, pz);
     M3 C = load_m3(s.C, p);
     {
@@ -203,29 +233,58 @@ mpm_p2g_kernel(const DevState s, const float dt) {
     }
     const float vol = s.vol[p];
     const int n = s.n_grid;
+
+    // runs of equal base cell among consecutive lanes, chopped at 8
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int key = contrib ? (W.bx * n + W.by) * n + W.bz : -1 - lane;
+    const int kprev = __shfl_up_sync(full, key, 1);
+    bool head = (lane == 0) || (key != kprev);
+    unsigned H = __ballot_sync(full, head);
+    const int hl = 31 - __clz(H & (0xffffffffu >> (31 - lane)));     // head lane of my run
+    head = head || (((lane - hl) & 7) == 0);
+    H = __ballot_sync(full, head);
+    const unsigned above = H & ~((2u << lane) - 1u);                  // heads strictly above this lane
+    const int seg_end = above ? (__ffs(above) - 2) : 31;              // last lane of my segment
+    const bool c1 = lane + 1 <= seg_end, c2 = lane + 2 <= seg_end, c4 = lane + 4 <= seg_end;
+    auto segsum = [&](float v) {
+        float t = __shfl_down_sync(full, v, 1); if (c1) v += t;
+        t = __shfl_down_sync(full, v, 2); if (c2) v += t;
+        t = __shfl_down_sync(full, v, 4); if (c4) v += t;
+        return v;
+    };
 #pragma unroll
-    for (int i = 0; i < 3; ++i)
+    for (int ii = 0; ii < (kSlices == 1 ? 3 : 1); ++ii) {
+        const int i = kSlices == 1 ? ii : (int)blockIdx.y;
+        // slice weights selected without dynamic indexing (keeps W in registers)
+        const float w0i = i == 0 ? W.w[0][0] : (i == 1 ? W.w[0][1] : W.w[0][2]);
+        const float dw0i = i == 0 ? W.dw[0][0] : (i == 1 ? W.dw[0][1] : W.dw[0][2]);
 #pragma unroll
         for (int j = 0; j < 3; ++j)
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
                 const int ix = W.bx + i, iy = W.by + j, iz = W.bz + k;
-                if ((unsigned)ix >= (unsigned)n || (unsigned)iy >= (unsigned)n || (unsigned)iz >= (unsigned)n)
-                    continue;   // the reference indexes out of bounds here (no checks); we drop the node
+                // the reference indexes out of bounds here (no checks); we drop the node. Same verdict for a whole run.
+                const bool inb = contrib && (unsigned)ix < (unsigned)n && (unsigned)iy < (unsigned)n && (unsigned)iz < (unsigned)n;
                 const V3 dpos = {((float)i - W.fx[0]) * s.dx, ((float)j - W.fx[1]) * s.dx, ((float)k - W.fx[2]) * s.dx};
-                const float weight = W.w[0][i] * W.w[1][j] * W.w[2][k];
-                const V3 dweight = {W.dw[0][i] * W.w[1][j] * W.w[2][k] * s.inv_dx,
-                                    W.w[0][i] * W.dw[1][j] * W.w[2][k] * s.inv_dx,
-                                    W.w[0][i] * W.w[1][j] * W.dw[2][k] * s.inv_dx};
+                const float weight = w0i * W.w[1][j] * W.w[2][k];
+                const V3 dweight = {dw0i * W.w[1][j] * W.w[2][k] * s.inv_dx,
+                                    w0i * W.dw[1][j] * W.w[2][k] * s.inv_dx,
+                                    w0i * W.w[1][j] * W.dw[2][k] * s.inv_dx};
                 const V3 sd = m3_mulv(tau, dweight);
                 const V3 cd = m3_mulv(C, dpos);
-                const float wm = weight * mass;
-                const float ax = wm * (vx + cd.x) + dt * (-vol * sd.x);
-                const float ay = wm * (vy + cd.y) + dt * (-vol * sd.y);
-                const float az = wm * (vz + cd.z) + dt * (-vol * sd.z);
-                float* node = reinterpret_cast<float*>(s.grid_mv + ((size_t)ix * n + iy) * n + iz);
-                ptx::red_add_v4(node, ax, ay, az, wm);
+                const float wm = inb ? weight * mass : 0.f;
+                float ax = inb ? wm * (vx + cd.x) + dt * (-vol * sd.x) : 0.f;
+                float ay = inb ? wm * (vy + cd.y) + dt * (-vol * sd.y) : 0.f;
+                float az = inb ? wm * (vz + cd.z) + dt * (-vol * sd.z) : 0.f;
+                float aw = wm;
+                ax = segsum(ax); ay = segsum(ay); az = segsum(az); aw = segsum(aw);
+                if (head && inb) {
+                    float* node = reinterpret_cast<float*>(s.grid_mv + ((size_t)ix * n + iy) * n + iz);
+                    ptx::red_add_v4(node, ax, ay, az, aw);
+                }
             }
+    }
 }
 
 // ------------------------------------------------------------------------------------------ grid
@@ -446,6 +505,16 @@ __global__ void mpm_select_cyl_kernel(const DevState s, float3 point, float3 nor
 
 #include "mpm_tiled.cuh"
 
+// base-cell key of every live particle (+ identity index), input of the radix sort that produces DevState::order
+__global__ void mpm_cell_key_kernel(const float* __restrict__ x, int n, float inv_dx, int n_grid, int* __restrict__ keys, int* __restrict__ idx) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const Weights W = bspline_t(inv_dx, x[3 * p], x[3 * p + 1], x[3 * p + 2]);
+    const int bx = min(max(W.bx, 0), n_grid - 1), by = min(max(W.by, 0), n_grid - 1), bz = min(max(W.bz, 0), n_grid - 1);
+    keys[p] = (bx * n_grid + by) * n_grid + bz;
+    idx[p] = p;
+}
+
 }  // namespace
 
 // ============================================================================================ host
@@ -468,6 +537,13 @@ struct Mpm {
     double graph_dt = 0;
     bool graph_valid = false;
     std::string error;
+
+    // ---- cell order for the warp-aggregated scatter (three-kernel path)
+    int *cell_order = nullptr, *cell_keys = nullptr, *cell_keys_sorted = nullptr, *cell_idx = nullptr;
+    void* cub_tmp = nullptr;
+    size_t cub_bytes = 0;
+    bool order_valid = false;
+    int steps_since_order = 0;
 
     // ---- tiled path (mpm_tiled.cuh)
     bool tiled = true;
@@ -502,6 +578,7 @@ static DevState make_state(Mpm* m) {
     s.lam = f(PIXIE_MPM_LAM); s.bulk = f(PIXIE_MPM_BULK); s.yield_stress = f(PIXIE_MPM_YIELD);
     s.material = reinterpret_cast<int*>(m->fields[PIXIE_MPM_MATERIAL]);
     s.selection = reinterpret_cast<int*>(m->fields[PIXIE_MPM_SELECTION]);
+    s.order = m->order_valid ? m->cell_order : nullptr;
     s.grid_mv = m->grid_mv; s.grid_v = m->grid_v; s.time = m->d_time; s.bcs = m->d_bcs; s.n_bc = (int)m->bcs.size();
     s.n = m->n_active; s.n_grid = m->n_grid;
     s.x_begin = m->x_begin; s.x_end = m->x_end;
@@ -513,6 +590,7 @@ static DevState make_state(Mpm* m) {
     s.rpic_damping = q.rpic_damping; s.grid_v_damping_scale = q.grid_v_damping_scale; s.alpha = q.alpha;
     s.hardening = q.hardening; s.xi = q.xi; s.plastic_viscosity = q.plastic_viscosity; s.softening = q.softening;
     s.update_cov_with_F = q.update_cov_with_F;
+    s.scatter_slices = getenv("PIXIE_MPM_SLICES") ? atoi(getenv("PIXIE_MPM_SLICES")) : 1;   // r01 A/B at 1e5 particles: 47.4 us (1) vs 51.1 us (3) per substep
     return s;
 }
 
@@ -717,6 +795,7 @@ Mpm* mpm_create(int n_particles, int n_grid, float grid_lim, std::string& err) {
 
 void mpm_destroy(Mpm* m) {
     if (!m) return;
+    cudaFree(m->cell_order); cudaFree(m->cell_keys); cudaFree(m->cell_keys_sorted); cudaFree(m->cell_idx); cudaFree(m->cub_tmp);
     for (void* p : m->tiled_allocs) cudaFree(p);
     if (m->graph) cudaGraphExecDestroy(m->graph);
     if (!m->grid_borrowed) cudaFree(m->grid_mv);
@@ -805,10 +884,42 @@ static int check_bound(Mpm* m) {
     return 0;
 }
 
+static constexpr int kReorderEvery = 100;   // substeps between re-sorts; CFL keeps a particle within ~a cell of its key for far longer
+
+// (Re)builds Mpm::cell_order from the current positions. Stream-ordered, no host sync: the graph reads the same buffer.
+static int mpm_build_cell_order(Mpm* m, cudaStream_t st) {
+    const int n = m->n_active;
+    if (n <= 0) { m->order_valid = false; return 0; }
+    int bits = 1;
+    while ((1ll << bits) < (long long)m->n_grid * m->n_grid * m->n_grid) ++bits;
+    if (!m->cell_order) {
+        const size_t cap = (size_t)m->n;
+        if (cudaMalloc(&m->cell_order, cap * sizeof(int)) != cudaSuccess || cudaMalloc(&m->cell_keys, cap * sizeof(int)) != cudaSuccess ||
+            cudaMalloc(&m->cell_keys_sorted, cap * sizeof(int)) != cudaSuccess || cudaMalloc(&m->cell_idx, cap * sizeof(int)) != cudaSuccess) {
+            m->error = "cudaMalloc failed (cell order)"; return 1;
+        }
+        cub::DeviceRadixSort::SortPairs(nullptr, m->cub_bytes, m->cell_keys, m->cell_keys_sorted, m->cell_idx, m->cell_order, (int)cap, 0, 32, st);
+        if (cudaMalloc(&m->cub_tmp, m->cub_bytes) != cudaSuccess) { m->error = "cudaMalloc failed (sort scratch)"; return 1; }
+    }
+    const float inv_dx = (float)((double)m->n_grid / (double)m->grid_lim);
+    mpm_cell_key_kernel<<<(n + 255) / 256, 256, 0, st>>>(reinterpret_cast<const float*>(m->fields[PIXIE_MPM_X]), n, inv_dx, m->n_grid, m->cell_keys, m->cell_idx);
+    size_t bytes = m->cub_bytes;
+    if (cub::DeviceRadixSort::SortPairs(m->cub_tmp, bytes, m->cell_keys, m->cell_keys_sorted, m->cell_idx, m->cell_order, n, 0, bits, st) != cudaSuccess) {
+        m->error = "radix sort failed"; return 1;
+    }
+    m->steps_since_order = 0;
+    if (!m->order_valid) { m->order_valid = true; m->graph_valid = false; }   // DevState::order changes from null to the buffer
+    return 0;
+}
+
 static void launch_substep(const DevState& s, float dt, double dt_d, cudaStream_t st) {
     const int n = s.n;
     const size_t nodes = (size_t)(s.x_end - s.x_begin) * s.n_grid * s.n_grid;
-    if (n > 0) mpm_p2g_kernel<<<(n + 127) / 128, 128, 0, st>>>(s, dt);
+    if (n > 0) {
+        mpm_stress_kernel<<<(n + 127) / 128, 128, 0, st>>>(s, dt);
+        if (s.scatter_slices == 3) mpm_scatter_kernel<3><<<dim3((n + 127) / 128, 3), 128, 0, st>>>(s, dt);
+        else mpm_scatter_kernel<1><<<(n + 127) / 128, 128, 0, st>>>(s, dt);
+    }
     mpm_grid_kernel<<<(unsigned)((nodes + 255) / 256), 256, 0, st>>>(s, dt);
     mpm_g2p_kernel<<<(std::max(n, 1) + 127) / 128, 128, 0, st>>>(s, dt, dt_d);
 }
@@ -823,6 +934,7 @@ int mpm_step(Mpm* m, int n_substeps, double dt_d, cudaStream_t st) {
         cudaMemcpy(m->d_time, &t, sizeof(double), cudaMemcpyHostToDevice);
     }
     const float dt = (float)dt_d;
+    if ((!m->order_valid || m->steps_since_order >= kReorderEvery) && mpm_build_cell_order(m, st)) return 1;
     const DevState s = make_state(m);
     int done = 0;
     if (n_substeps >= kGraphSteps) {
@@ -845,12 +957,14 @@ int mpm_step(Mpm* m, int n_substeps, double dt_d, cudaStream_t st) {
         }
         if (m->graph_valid) {
             while (n_substeps - done >= kGraphSteps) {
+                if (m->steps_since_order >= kReorderEvery && mpm_build_cell_order(m, st)) return 1;
                 if (cudaGraphLaunch(m->graph, st) != cudaSuccess) { m->error = "cudaGraphLaunch failed"; return 1; }
                 done += kGraphSteps;
+                m->steps_since_order += kGraphSteps;
             }
         }
     }
-    for (; done < n_substeps; ++done) launch_substep(s, dt, dt_d, st);
+    for (; done < n_substeps; ++done) { launch_substep(s, dt, dt_d, st); ++m->steps_since_order; }
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { m->error = std::string("kernel launch failed: ") + cudaGetErrorString(e); return 1; }
     return 0;
@@ -918,6 +1032,7 @@ int mpm_set_active_count(Mpm* m, int n_active) {
     if (n_active < 0 || n_active > m->n) { m->error = "active count exceeds the bound capacity"; return 1; }
     if (mpm_sync(m, 0)) return 1;
     m->n_active = n_active;
+    m->order_valid = false;       // the order lists exactly the live prefix
     m->graph_valid = false;
     return 0;
 }
@@ -925,7 +1040,11 @@ int mpm_substep_scatter(Mpm* m, double dt_d, cudaStream_t st) {
     if (m->tiled) { m->error = "split substeps are not available on the tiled path"; return 1; }
     if (check_bound(m)) return 1;
     const DevState s = make_state(m);
-    if (s.n > 0) mpm_p2g_kernel<<<(s.n + 127) / 128, 128, 0, st>>>(s, (float)dt_d);
+    if (s.n > 0) {
+        mpm_stress_kernel<<<(s.n + 127) / 128, 128, 0, st>>>(s, (float)dt_d);
+        if (s.scatter_slices == 3) mpm_scatter_kernel<3><<<dim3((s.n + 127) / 128, 3), 128, 0, st>>>(s, (float)dt_d);
+        else mpm_scatter_kernel<1><<<(s.n + 127) / 128, 128, 0, st>>>(s, (float)dt_d);
+    }
     return cudaGetLastError() != cudaSuccess;
 }
 int mpm_substep_finish(Mpm* m, double dt_d, cudaStream_t st) {
