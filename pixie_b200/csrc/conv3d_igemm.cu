@@ -50,6 +50,20 @@ __device__ __forceinline__ float warp_colsum16(float (&v)[16], int lane) {
     }
     return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
 }
+// Same for 32 channels: after the five halving steps lane l holds the column sum of channel l. 31 shuffles.
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+    for (int half = 16, off = 16; half >= 1; half >>= 1, off >>= 1) {
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+            const float keep = up ? v[i + half] : v[i];
+            const float send = up ? v[i] : v[i + half];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    return v[0];
+}
 __device__ __forceinline__ int stats_channel_of_lane(int lane) {
     return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
 }
@@ -431,80 +445,99 @@ conv3d_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
             const int hh = t.h0 + th, ww = t.w0 + tw;
             const bool row_ok = (hh < p.H) && (ww < p.W);
             const bool first_split = (t.split == 0);
-            for (int d = 0; d < t.tde && !(p.debug_flags & 1); ++d) {
-                const long long vox = ((long long)(t.d0 + d) * p.H + hh) * p.W + ww;   // inside batch item
-                const uint32_t acc = tmem_base + ((uint32_t)(q * 32) << 16) +
-                                     (uint32_t)((as * TD + d) * block_n);
-                int c = 0;
-                // ---- wide path: 64 channels per step. One warp per scheduler means nothing hides latency but the
-                // warp's own ILP: both TMEM loads and all 16 residual loads are in flight before the first use.
-                for (; wide_ok && c + 64 <= block_n && t.n0 + c + 64 <= p.Cout; c += 64) {
-                    const int ch0 = t.n0 + c;
-                    uint32_t v[64];
-                    tmem_ld32(acc + (uint32_t)c, v);
-                    tmem_ld32(acc + (uint32_t)c + 32u, v + 32);
-                    const long long base = ((long long)t.nb * DHW + vox) * p.out_ld + p.out_c0 + ch0;
-                    const bool use_res = row_ok && first_split && p.residual != nullptr;
-                    float4 rv[16];
-                    if (use_res) {
-                        const float4* rp = reinterpret_cast<const float4*>(p.residual + base);
+            // ---- wide path: 32-channel chunks, chunk-outer / plane-inner, two planes in flight. One warp per scheduler means
+            // nothing hides latency but the warp's own ILP, so both TMEM loads and all residual loads are issued before
+            // the first use. Per-channel statistics are accumulated per thread over the tile's planes and reduced across
+            // the warp ONCE per (tile, chunk): the per-plane shuffle reduction cost 10 % of a 64->64 conv (r01) and its
+            // 250 shuffles per plane competed with the MMA issuer for the MIO queue.
+            int c_wide = 0;
+            if (wide_ok && !(p.debug_flags & 1)) {
+                const bool use_bias = first_split && p.bias != nullptr;
+                const bool use_res = row_ok && first_split && p.residual != nullptr;
+                const long long plane_ld = (long long)p.H * p.W * p.out_ld;
+                for (; c_wide + 32 <= block_n && t.n0 + c_wide + 32 <= p.Cout; c_wide += 32) {
+                    const int ch0 = t.n0 + c_wide;
+                    float cs[32], cq[32];
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) rv[j] = __ldg(rp + j);
-                    }
-                    float4 bv[16];
-                    const bool use_bias = first_split && p.bias != nullptr;
-                    if (use_bias) {
-                        const float4* bp = reinterpret_cast<const float4*>(p.bias + ch0);
+                    for (int j = 0; j < 32; ++j) { cs[j] = 0.f; cq[j] = 0.f; }
+                    auto finish = [&](uint32_t (&v)[32], float4 (&r)[8], long long base) {
+                        float f[32];
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) bv[j] = __ldg(bp + j);
-                    }
-                    tmem_ld_wait();
-                    float f[64];
+                        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+                        if (use_bias) {
+                            const float4* bp = reinterpret_cast<const float4*>(p.bias + ch0);
 #pragma unroll
-                    for (int j = 0; j < 64; ++j) f[j] = __uint_as_float(v[j]);
-                    if (use_bias) {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            f[4 * j + 0] += bv[j].x; f[4 * j + 1] += bv[j].y;
-                            f[4 * j + 2] += bv[j].z; f[4 * j + 3] += bv[j].w;
+                            for (int j = 0; j < 8; ++j) {
+                                const float4 b = __ldg(bp + j);
+                                f[4 * j + 0] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w;
+                            }
                         }
-                    }
-                    if (use_res) {
+                        if (use_res) {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            f[4 * j + 0] += rv[j].x; f[4 * j + 1] += rv[j].y;
-                            f[4 * j + 2] += rv[j].z; f[4 * j + 3] += rv[j].w;
+                            for (int j = 0; j < 8; ++j) {
+                                f[4 * j + 0] += r[j].x; f[4 * j + 1] += r[j].y; f[4 * j + 2] += r[j].z; f[4 * j + 3] += r[j].w;
+                            }
                         }
-                    }
-                    if (row_ok) {
-                        if (p.atomic_out) {
+                        if (row_ok) {
+                            if (p.atomic_out) {
 #pragma unroll
-                            for (int j = 0; j < 16; ++j)
-                                red_add_v4(p.out + base + 4 * j, f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-                        } else {
-                            float4* op = reinterpret_cast<float4*>(p.out + base);
+                                for (int j = 0; j < 8; ++j)
+                                    red_add_v4(p.out + base + 4 * j, f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                            } else {
+                                float4* op = reinterpret_cast<float4*>(p.out + base);
 #pragma unroll
-                            for (int j = 0; j < 16; ++j)
-                                op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                                for (int j = 0; j < 8; ++j)
+                                    op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                            }
+                            if (do_stats) {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) { cs[j] += f[j]; cq[j] = fmaf(f[j], f[j], cq[j]); }
+                            }
                         }
+                    };
+                    for (int d = 0; d < t.tde; d += 2) {
+                        const bool two = d + 1 < t.tde;                 // warp-uniform
+                        const uint32_t acc0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((as * TD + d) * block_n + c_wide);
+                        uint32_t v0[32], v1[32];
+                        tmem_ld32(acc0, v0);
+                        if (two) tmem_ld32(acc0 + (uint32_t)block_n, v1);
+                        const long long base0 = ((long long)t.nb * DHW + ((long long)(t.d0 + d) * p.H + hh) * p.W + ww) * p.out_ld + p.out_c0 + ch0;
+                        float4 r0[8], r1[8];
+                        if (use_res) {
+                            const float4* rp = reinterpret_cast<const float4*>(p.residual + base0);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) r0[j] = __ldg(rp + j);
+                            if (two) {
+                                const float4* rq = reinterpret_cast<const float4*>(p.residual + base0 + plane_ld);
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) r1[j] = __ldg(rq + j);
+                            }
+                        }
+                        tmem_ld_wait();
+                        finish(v0, r0, base0);
+                        if (two) finish(v1, r1, base0 + plane_ld);
                     }
                     if (do_stats) {
                         if (scalar_stats) {
                             float s = 0.f, q2 = 0.f;
 #pragma unroll
-                            for (int j = 0; j < 64; ++j) { s += f[j]; q2 = fmaf(f[j], f[j], q2); }
-                            if (row_ok) { tot_s += (double)s; tot_q += (double)q2; }
+                            for (int j = 0; j < 32; ++j) { s += cs[j]; q2 += cq[j]; }
+                            tot_s += (double)s; tot_q += (double)q2;
                         } else {
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                float g[16];
-#pragma unroll
-                                for (int j = 0; j < 16; ++j) g[j] = row_ok ? f[16 * k + j] : 0.f;
-                                add_stats16(g, ch0 + 16 * k);
-                            }
+                            const float s1 = warp_colsum32(cs, lane);       // lane l ends up with channel ch0 + l
+                            const float s2 = warp_colsum32(cq, lane);
+                            my_stats[ch0 + lane] += s1;
+                            my_stats[kStatsMaxC + ch0 + lane] += s2;
+                            __syncwarp();
                         }
                     }
                 }
+            }
+            for (int d = 0; d < t.tde && !(p.debug_flags & 1); ++d) {
+                const long long vox = ((long long)(t.d0 + d) * p.H + hh) * p.W + ww;   // inside batch item
+                const uint32_t acc = tmem_base + ((uint32_t)(q * 32) << 16) +
+                                     (uint32_t)((as * TD + d) * block_n);
+                int c = c_wide;
                 // ---- generic path: 16 channels per step (ragged Cout, planar outputs, narrow tiles)
                 for (; c < block_n; c += 16) {
                     uint32_t v[16];

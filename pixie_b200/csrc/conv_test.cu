@@ -130,7 +130,7 @@ int main(int argc, char** argv) {
         double* d_stats = nullptr;
         CK(cudaMalloc(&d_stats, (size_t)c.NB * c.Cout * 2 * sizeof(double)));
         CK(cudaMemset(d_stats, 0, (size_t)c.NB * c.Cout * 2 * sizeof(double)));
-        d.stats = d_stats;
+        d.stats = getenv("CONV_TEST_NO_STATS") ? nullptr : d_stats;
         const bool scalar_stats = getenv("CONV_TEST_SCALAR_STATS") != nullptr;   // totals-only mode of the fused statistics
         d.stats_scalar = scalar_stats;
 
