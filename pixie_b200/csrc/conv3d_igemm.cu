@@ -32,8 +32,7 @@ struct SmemCtrl {
 constexpr int kPhasesSmemMax = 256;       // phase table copied to shared memory when it fits (4 KB)
 constexpr int kCtlBarrierBytes = 512;     // SmemCtrl
 constexpr int kStatsMaxC = 256;
-// per epilogue warp: [2][kStatsMaxC] floats (sum, sum of squares), private to the warp -> no atomics
-constexpr int kStatsSmemBytes = 4 * 2 * kStatsMaxC * 4;
+// per epilogue warp: [2][stats_ld] floats (sum, sum of squares), private to the warp -> no atomics
 
 // Reduces v[0..15] (16 channels held by every lane = one voxel row each) over the 32 lanes of the warp.
 // Returns, in every lane, the column sum of channel stats_channel_of_lane(lane). 16 shuffles.
@@ -182,14 +181,18 @@ conv3d_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
     // dynamic smem base is only guaranteed 16 B aligned by the ABI: align manually to 1024 B
     uint8_t* smem = reinterpret_cast<uint8_t*>(
         (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    // plans without alignment slack (p.smem_slack == 0) rely on the 1 KB-aligned dynamic smem base that kernels without
+    // static shared memory get in practice; verified here, failing loudly through the error flag instead of corrupting smem
+    const bool smem_misaligned = (p.smem_slack == 0) && (smem != smem_raw);
     uint8_t* w_smem = smem;
     uint8_t* s_smem = smem + (size_t)p.w_stages * p.w_stage_bytes;
     SmemCtrl* ctl = reinterpret_cast<SmemCtrl*>(s_smem + (size_t)p.s_stages * p.s_stage_bytes);
     ConvPhase* phases_sm = reinterpret_cast<ConvPhase*>(reinterpret_cast<uint8_t*>(ctl) + kCtlBarrierBytes);
-    float* stats_sm = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(phases_sm) + kPhasesSmemMax * sizeof(ConvPhase));   // used iff p.stats
+    float* stats_sm = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(phases_sm) + p.phases_smem_bytes);   // used iff p.stats
+    const int stats_ld = p.stats_ld;     // channels per statistics row (Cout rounded up to 32)
     // The producer and the MMA issuer read one descriptor per phase on their critical path: from shared memory that is
     // ~30 cycles, from global ~800 (a phase is only TD+2 slabs long).
-    const bool phases_in_smem = p.n_phases <= kPhasesSmemMax;
+    const bool phases_in_smem = p.phases_smem_bytes > 0;
     if (phases_in_smem)
         for (int i = threadIdx.x; i < p.n_phases; i += blockDim.x) phases_sm[i] = p.phases[i];
     const ConvPhase* phases = phases_in_smem ? phases_sm : p.phases;
@@ -205,7 +208,7 @@ conv3d_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
         for (int i = 0; i < kMaxWStages; ++i) { mbar_init(&ctl->wfull[i], 1); mbar_init(&ctl->wempty[i], 1); }
         for (int i = 0; i < kMaxSStages; ++i) { mbar_init(&ctl->sfull[i], 1); mbar_init(&ctl->sempty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&ctl->tfull[i], 1); mbar_init(&ctl->tempty[i], 4); }
-        ctl->abort_flag = 0;
+        ctl->abort_flag = smem_misaligned ? 1 : 0;
         fence_barrier_init();
     }
     if (warp == 1) {
@@ -369,12 +372,12 @@ conv3d_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
         const long long DHW = (long long)p.D * p.H * p.W;
         const bool do_stats = p.stats != nullptr;
         const bool scalar_stats = do_stats && p.stats_scalar;     // consumer only needs the per-item totals (LayerNorm)
-        float* my_stats = stats_sm + (size_t)(warp - 2) * 2 * kStatsMaxC;
+        float* my_stats = stats_sm + (size_t)(warp - 2) * 2 * stats_ld;
         const int et = threadIdx.x - 64;        // 0..127 among the epilogue threads
         int stats_nb = -1;
         double tot_s = 0.0, tot_q = 0.0;        // scalar mode: this thread's running totals
         if (do_stats && !scalar_stats) {
-            for (int i = lane; i < 2 * kStatsMaxC; i += 32) my_stats[i] = 0.f;
+            for (int i = lane; i < 2 * stats_ld; i += 32) my_stats[i] = 0.f;
             __syncwarp();
         }
         auto flush_stats = [&](int nb) {
@@ -398,14 +401,14 @@ conv3d_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
                 float s = 0.f, qq = 0.f;
 #pragma unroll
                 for (int w = 0; w < 4; ++w) {
-                    s += stats_sm[(size_t)w * 2 * kStatsMaxC + ch];
-                    qq += stats_sm[(size_t)w * 2 * kStatsMaxC + kStatsMaxC + ch];
+                    s += stats_sm[(size_t)w * 2 * stats_ld + ch];
+                    qq += stats_sm[(size_t)w * 2 * stats_ld + stats_ld + ch];
                 }
                 atomicAdd(p.stats + ((size_t)nb * p.Cout + ch) * 2, (double)s);
                 atomicAdd(p.stats + ((size_t)nb * p.Cout + ch) * 2 + 1, (double)qq);
             }
             asm volatile("bar.sync 1, 128;" ::: "memory");
-            for (int i = lane; i < 2 * kStatsMaxC; i += 32) my_stats[i] = 0.f;
+            for (int i = lane; i < 2 * stats_ld; i += 32) my_stats[i] = 0.f;
             __syncwarp();
         };
         // f[0..15] = final values of 16 channels of this thread's voxel row (zero where invalid)
@@ -425,7 +428,7 @@ conv3d_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
             const int chn = ch0 + stats_channel_of_lane(lane);
             if ((lane & 1) == 0 && chn < p.Cout) {
                 my_stats[chn] += s1;
-                my_stats[kStatsMaxC + chn] += s2;
+                my_stats[stats_ld + chn] += s2;
             }
             __syncwarp();
         };
@@ -527,7 +530,7 @@ conv3d_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
                             const float s1 = warp_colsum32(cs, lane);       // lane l ends up with channel ch0 + l
                             const float s2 = warp_colsum32(cq, lane);
                             my_stats[ch0 + lane] += s1;
-                            my_stats[kStatsMaxC + ch0 + lane] += s2;
+                            my_stats[stats_ld + ch0 + lane] += s2;
                             __syncwarp();
                         }
                     }
@@ -888,22 +891,26 @@ int conv_plan_create(const ConvDesc& d, int* d_err_flag, ConvPlan& plan, char* e
     for (size_t i = 0; i < slots.size(); ++i) max_rows = std::max(max_rows, p.slab_rows[i]);
     p.w_stage_bytes = max_taps * bn * 128;
     p.s_stage_bytes = max_rows * 128;
-    const int avail = 227 * 1024 - (1024 + kCtlBarrierBytes + kPhasesSmemMax * (int)sizeof(ConvPhase));   // alignment slack + control block
-    p.w_stages = (2 * p.w_stage_bytes + 2 * p.s_stage_bytes <= avail) ? 2 : 1;
-    if (p.w_stages * p.w_stage_bytes + 2 * p.s_stage_bytes > avail) return fail("tile does not fit in shared memory");
-    p.s_stages = std::min(kMaxSStages, (avail - p.w_stages * p.w_stage_bytes) / p.s_stage_bytes);
-    p.s_stages = std::min(p.s_stages, 6);
+    // control block: barriers + phase table (when it fits 4 KB) + per-warp statistics rows; the 1 KB alignment slack is
+    // dropped when exactly that buys another slab stage (the kernel then verifies the base alignment itself)
     plan.fused_stats = d.stats != nullptr && split == 1 && d.Cout <= kStatsMaxC && !d.out_planar;
-    // 1 KB slack for the manual 1024 B alignment of the dynamic smem base + barriers + phase table (+ statistics scratch)
-    const int ctl_bytes = 1024 + kCtlBarrierBytes + kPhasesSmemMax * (int)sizeof(ConvPhase) + (plan.fused_stats ? kStatsSmemBytes : 0);
-    {
-        const int avail2 = 227 * 1024 - ctl_bytes;
-        while (p.s_stages > 2 && p.w_stages * p.w_stage_bytes + p.s_stages * p.s_stage_bytes > avail2) --p.s_stages;
-        if (p.w_stages * p.w_stage_bytes + p.s_stages * p.s_stage_bytes > avail2) {
-            if (p.w_stages == 2) p.w_stages = 1;
-        }
-        if (p.w_stages * p.w_stage_bytes + p.s_stages * p.s_stage_bytes > avail2) return fail("no room for the statistics scratch");
-    }
+    p.phases_smem_bytes = p.n_phases <= kPhasesSmemMax ? (p.n_phases * (int)sizeof(ConvPhase) + 127) / 128 * 128 : 0;
+    p.stats_ld = (d.Cout + 31) / 32 * 32;
+    const int stats_bytes = plan.fused_stats ? 4 * 2 * p.stats_ld * 4 : 0;
+    const int ctl_core = kCtlBarrierBytes + p.phases_smem_bytes + stats_bytes;
+    auto plan_stages = [&](int slack, int& ws, int& ss) {
+        const int avail = 227 * 1024 - ctl_core - slack;
+        ws = (2 * p.w_stage_bytes + 2 * p.s_stage_bytes <= avail) ? 2 : 1;
+        if (ws * p.w_stage_bytes + 2 * p.s_stage_bytes > avail) return false;
+        ss = std::min(std::min(kMaxSStages, 6), (avail - ws * p.w_stage_bytes) / p.s_stage_bytes);
+        return true;
+    };
+    int ws1 = 0, ss1 = 0, ws0 = 0, ss0 = 0;
+    const bool ok1 = plan_stages(1024, ws1, ss1), ok0 = plan_stages(0, ws0, ss0);
+    if (!ok0) return fail("tile does not fit in shared memory");
+    if (ok1 && ws1 >= ws0 && ss1 >= ss0) { p.smem_slack = 1024; p.w_stages = ws1; p.s_stages = ss1; }
+    else { p.smem_slack = 0; p.w_stages = ws0; p.s_stages = ss0; }
+    const int ctl_bytes = ctl_core + p.smem_slack;
     plan.smem_bytes = p.w_stages * p.w_stage_bytes + p.s_stages * p.s_stage_bytes + ctl_bytes;
 
     if (encode_a_maps(d, p, enc, err, errlen)) return 1;
@@ -939,7 +946,7 @@ int conv_plan_create(const ConvDesc& d, int* d_err_flag, ConvPlan& plan, char* e
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     plan.grid = std::min(items * split, sms);
 
-    plan.variant = conv_variant_index(p.block_n, p.TW, p.TD);
+    plan.variant = getenv("PIXIE_CONV_GENERIC") ? 0 : conv_variant_index(p.block_n, p.TW, p.TD);   // env: bring-up A/B
     static bool attr_set = false;
     if (!attr_set) {
         for (int v = 0; v < kNumConvVariants; ++v)

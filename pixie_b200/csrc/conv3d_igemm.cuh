@@ -74,6 +74,9 @@ struct ConvKernelParams {
     int atomic_out;          // 1: red.add into out (split_k > 1); out must be pre-zeroed
     double* stats;           // optional [NB][Cout][2] = (sum, sum of squares) of the outputs over voxels,
                              // accumulated by the epilogue (fused LayerNorm/GroupNorm statistics); or nullptr
+    int stats_ld;            // floats per statistics row in shared memory (Cout rounded up to 32)
+    int phases_smem_bytes;   // size of the phase table copy in shared memory (0: read phases from global)
+    int smem_slack;          // bytes reserved for aligning the dynamic smem base to 1 KB (0: the base must already be aligned)
     int stats_scalar;        // 1: only the per-item totals are wanted; they land in channel 0's slot (LayerNorm consumers)
     int* err_flag;           // device int, set non-zero on pipeline timeout
     uint64_t desc_xor;       // bring-up only: xor into every smem matrix descriptor (0 in product use)

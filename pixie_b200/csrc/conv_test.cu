@@ -196,7 +196,8 @@ int main(int argc, char** argv) {
             cudaEventElapsedTime(&ms, e0, e1);
             ms /= iters;
             double flops = 2.0 * vox_out * c.Cout * (double)conv_k_total(d);
-            printf("[%s] TIME %.3f ms  %.1f TFLOP/s (padded-K flops)\n", c.name.c_str(), ms, flops / ms * 1e-9);
+            printf("[%s] TIME %.3f ms  %.1f TFLOP/s (padded-K flops)  [bn=%d TW=%d TD=%d w_stages=%d s_stages=%d split=%d smem=%d]\n", c.name.c_str(), ms, flops / ms * 1e-9,
+                   plan.p.block_n, plan.p.TW, plan.p.TD, plan.p.w_stages, plan.p.s_stages, plan.p.split_k, plan.smem_bytes);
         }
 
         // verification (sampled voxels for big cases)
