@@ -26,10 +26,6 @@ struct SmemCtrl {
     int abort_flag;
 };
 
-// bring-up event log: role r appends (clock64 << 8 | code) to trace[r * 4096 + n]
-#define PIXIE_TR(tr_, role_, n_, code_) do { if ((tr_) && (n_) < 4096) { (tr_)[(role_) * 4096 + (n_)] = (clock64() << 8) | (long long)(code_); ++(n_); } } while (0)
-
-constexpr int kPhasesSmemMax = 256;       // phase table copied to shared memory when it fits (4 KB)
 constexpr int kCtlBarrierBytes = 512;     // SmemCtrl
 constexpr int kStatsMaxC = 256;
 // per epilogue warp: [2][stats_ld] floats (sum, sum of squares), private to the warp -> no atomics
@@ -71,7 +67,7 @@ struct TileCoord {
     int nb, d0, h0, w0, n0, ph_begin, ph_end, split, tde;
 };
 
-__device__ __forceinline__ TileCoord decode_tile(const ConvKernelParams& p, int wi, int block_n, int TW, int TD) {
+__device__ __forceinline__ TileCoord decode_tile(const ConvKernelParams& p, int wi) {
     TileCoord t;
     t.split = wi % p.split_k;
     int rest = wi / p.split_k;
@@ -83,13 +79,13 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvKernelParams& p, int 
     m /= p.tiles_h;
     int td = m % p.tiles_d;
     t.nb = m / p.tiles_d;
-    t.d0 = td * TD;
-    t.h0 = th * (128 / TW);
-    t.w0 = tw * TW;
-    t.n0 = nt * block_n;
+    t.d0 = td * p.TD;
+    t.h0 = th * p.TH;
+    t.w0 = tw * p.TW;
+    t.n0 = nt * p.block_n;
     t.ph_begin = (int)(((long long)t.split * p.n_phases) / p.split_k);
     t.ph_end = (int)(((long long)(t.split + 1) * p.n_phases) / p.split_k);
-    t.tde = min(TD, p.D - t.d0);
+    t.tde = min(p.TD, p.D - t.d0);
     return t;
 }
 
@@ -101,7 +97,7 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvKernelParams& p, int 
 // (r01: 240 instructions per slab at ~7 cycles each vs 12 x 96 tensor-pipe cycles).
 template <int BN, int TWv>
 __device__ __forceinline__ void issue_slab_3x3(uint32_t acc0, uint32_t a_lo0, uint32_t b_lo0, uint32_t hi, uint32_t idA,
-                                               uint32_t id_old, uint32_t id1, int nold, bool fresh, bool only_first) {
+                                               uint32_t id_old, uint32_t id1, int nold, bool fresh) {
     constexpr uint32_t kKh = (uint32_t)(TWv * 128) >> 4, kTap = (uint32_t)(BN * 128) >> 4;
     if (fresh) {
         // the newest plane's accumulator is overwritten by its first MMA, the older planes accumulate
@@ -110,7 +106,6 @@ __device__ __forceinline__ void issue_slab_3x3(uint32_t acc0, uint32_t a_lo0, ui
     } else {
         umma_f16_lohi<true>(acc0, a_lo0, b_lo0, hi, idA);
     }
-    if (only_first) return;      // bring-up timing experiment (debug_flags bit 2)
 #pragma unroll
     for (int i = 1; i < 12; ++i) {
         const uint32_t kh = (uint32_t)(i >> 2), k4 = (uint32_t)(i & 3);
@@ -118,89 +113,25 @@ __device__ __forceinline__ void issue_slab_3x3(uint32_t acc0, uint32_t a_lo0, ui
     }
 }
 
-// A whole 3x3x3 stride-1 phase of a full-depth tile (TDv output planes, TDv + 2 input slabs), issued by ONE elected thread
-// with the plane loop unrolled: which accumulators / weight blocks a slab feeds is a compile-time fact, so a slab costs the
-// issuing thread its barrier wait, ~5 uniform-datapath instructions per MMA and a commit. The per-slab bookkeeping of the
-// generic loop (~150 instructions, ~800 cycles on one warp) was the kernel's critical path (r01 timing experiments).
-// Returns false if a barrier timed out. `ss`/`sph` (slab ring position) are advanced identically in every lane.
-template <int BN, int TWv, int TDv>
-__device__ __forceinline__ bool mma_phase_3x3(SmemCtrl* ctl, int s_stages, uint32_t s_stage_bytes, int& ss, int& sph, uint32_t s_base0,
-                                              uint32_t w16, uint32_t acc_set, bool first_phase, uint32_t desc_lo, uint32_t desc_hi,
-                                              bool only_first, volatile int* abort_flag, long long* trace, int& ntr) {
-    constexpr uint32_t kTap = (uint32_t)(BN * 128) >> 4;
-    constexpr uint32_t id1 = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | (8u << 24);
-    constexpr uint32_t id2 = (1u << 4) | ((uint32_t)((2 * BN) >> 3) << 17) | (8u << 24);
-    constexpr uint32_t id3 = (1u << 4) | ((uint32_t)((3 * BN) >> 3) << 17) | (8u << 24);
-    bool ok = true;
-    const bool leader = elect_one();
-    if (leader) {
-        int s = ss, sp = sph;
-#pragma unroll
-        for (int pl = 0; pl < TDv + 2; ++pl) {
-            const int d_min = pl - 2 > 0 ? pl - 2 : 0, d_max = pl < TDv - 1 ? pl : TDv - 1;
-            const int nblk = d_max - d_min + 1, kd_hi = pl - d_min, nold = nblk - 1;
-            const uint32_t idA = nblk == 1 ? id1 : (nblk == 2 ? id2 : id3);
-            const uint32_t id_old = nold == 1 ? id1 : id2;
-            if (ok) {
-                PIXIE_TR(trace, 1, ntr, 3);
-                ok = mbar_wait(&ctl->sfull[s], (uint32_t)sp, abort_flag);
-                if (ok) {
-                    PIXIE_TR(trace, 1, ntr, 4);
-                    tc_fence_after();
-                    const uint32_t s16 = (s_base0 + (uint32_t)s * s_stage_bytes) >> 4;
-                    issue_slab_3x3<BN, TWv>(acc_set + (uint32_t)(d_min * BN), desc_lo | (s16 & 0x3FFFu),
-                                            desc_lo | ((w16 + (uint32_t)(2 - kd_hi) * kTap) & 0x3FFFu), desc_hi, idA, id_old, id1,
-                                            nold, first_phase && d_max == pl, only_first);
-                    umma_commit(&ctl->sempty[s]);        // slab slot free once these MMAs retire
-                    PIXIE_TR(trace, 1, ntr, 5);
-                    if (++s == s_stages) { s = 0; sp ^= 1; }
-                }
-            }
-        }
-    }
-    PIXIE_TR(leader ? trace : nullptr, 1, ntr, 15);      // (elect.sync picks lane 0 of a converged warp: same lane as the caller's log)
-    __syncwarp();
-    ok = (*abort_flag == 0);            // a timed-out wait in the elected lane raised the CTA-wide flag
-    PIXIE_TR(leader ? trace : nullptr, 1, ntr, 16);
-    int s = ss + TDv + 2;
-    while (s >= s_stages) { s -= s_stages; sph ^= 1; }
-    ss = s;
-    return ok;
-}
-
-// kBN / kTW / kTD = 0: generic kernel (everything read from the parameters). Non-zero: specialised for that tile shape --
-// loop bounds become constants and the MMA role contains ONE unrolled 3x3x3 phase issuer instead of a dispatch over twelve
-// (the all-in-one kernel was 240 KB of SASS with a 86 % instruction-cache hit rate; r01 profile).
-template <int kBN, int kTW, int kTD>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv3d_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
-    const int block_n = kBN ? kBN : p.block_n;
-    const int TW = kTW ? kTW : p.TW;
-    const int TD = kTD ? kTD : p.TD;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // dynamic smem base is only guaranteed 16 B aligned by the ABI: align manually to 1024 B
     uint8_t* smem = reinterpret_cast<uint8_t*>(
         (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-    // plans without alignment slack (p.smem_slack == 0) rely on the 1 KB-aligned dynamic smem base that kernels without
-    // static shared memory get in practice; verified here, failing loudly through the error flag instead of corrupting smem
-    const bool smem_misaligned = (p.smem_slack == 0) && (smem != smem_raw);
     uint8_t* w_smem = smem;
     uint8_t* s_smem = smem + (size_t)p.w_stages * p.w_stage_bytes;
     SmemCtrl* ctl = reinterpret_cast<SmemCtrl*>(s_smem + (size_t)p.s_stages * p.s_stage_bytes);
-    ConvPhase* phases_sm = reinterpret_cast<ConvPhase*>(reinterpret_cast<uint8_t*>(ctl) + kCtlBarrierBytes);
-    float* stats_sm = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(phases_sm) + p.phases_smem_bytes);   // used iff p.stats
+    float* stats_sm = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ctl) + kCtlBarrierBytes);   // used iff p.stats
     const int stats_ld = p.stats_ld;     // channels per statistics row (Cout rounded up to 32)
-    // The producer and the MMA issuer read one descriptor per phase on their critical path: from shared memory that is
-    // ~30 cycles, from global ~800 (a phase is only TD+2 slabs long).
-    const bool phases_in_smem = p.phases_smem_bytes > 0;
-    if (phases_in_smem)
-        for (int i = threadIdx.x; i < p.n_phases; i += blockDim.x) phases_sm[i] = p.phases[i];
-    const ConvPhase* phases = phases_in_smem ? phases_sm : p.phases;
+    // plans without alignment slack (p.smem_slack == 0) rely on the 1 KB-aligned dynamic smem base that kernels without
+    // static shared memory get in practice; verified here, failing loudly through the error flag instead of corrupting smem
+    const bool smem_misaligned = (p.smem_slack == 0) && (smem != smem_raw);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int total_items = p.NB * p.tiles_d * p.tiles_h * p.tiles_w * p.n_tiles * p.split_k;
-    const uint32_t tmem_cols_needed = (uint32_t)(p.acc_sets * TD * block_n);
+    const uint32_t tmem_cols_needed = (uint32_t)(p.acc_sets * p.TD * p.block_n);
     uint32_t tmem_cols = 32;
     while (tmem_cols < tmem_cols_needed) tmem_cols <<= 1;
 
@@ -229,23 +160,20 @@ conv3d_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
         // ================================================================ TMA producer (warp-uniform, one elected lane issues)
         int ws = 0, wph = 0, ss = 0, sph = 0;
         int wcount = 0, scount = 0;     // bring-up only (debug_flags bit 1: stop re-loading once every stage was filled)
-        long long* tr = (blockIdx.x == 0 && lane == 0) ? p.trace : nullptr; int ntr = 0;
         bool ok = true;
         for (int wi = blockIdx.x; wi < total_items && ok; wi += gridDim.x) {
-            const TileCoord t = decode_tile(p, wi, block_n, TW, TD);
+            const TileCoord t = decode_tile(p, wi);
             for (int ph = t.ph_begin; ph < t.ph_end && ok; ++ph) {
-                const ConvPhase P = phases[ph];
+                const ConvPhase P = p.phases[ph];
                 const int ntaps = P.n_kh * P.n_kd;
-                PIXIE_TR(tr, 0, ntr, 1);
                 ok = mbar_wait(&ctl->wempty[ws], wph ^ 1, abort_flag);
                 if (!ok) break;
-                PIXIE_TR(tr, 0, ntr, 2);
                 if ((p.debug_flags & 2) && wcount >= p.w_stages) { if (elect_one()) mbar_arrive(&ctl->wfull[ws]); }
                 else if (elect_one()) {
-                    mbar_expect_tx(&ctl->wfull[ws], (uint32_t)(ntaps * block_n * 128));
+                    mbar_expect_tx(&ctl->wfull[ws], (uint32_t)(ntaps * p.block_n * 128));
                     uint8_t* wdst = w_smem + (size_t)ws * p.w_stage_bytes;
                     for (int tap = 0; tap < ntaps; ++tap)
-                        tma_load_2d(wdst + (size_t)tap * block_n * 128, &p.tmB, &ctl->wfull[ws],
+                        tma_load_2d(wdst + (size_t)tap * p.block_n * 128, &p.tmB, &ctl->wfull[ws],
                                     (P.wtile_base + tap) * 64, t.n0);
                 }
                 ++wcount;
@@ -254,10 +182,8 @@ conv3d_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
                 const int nplanes = t.tde + P.n_kd - 1;
                 const uint32_t slab_bytes = (uint32_t)p.slab_rows[P.src] * 128u;
                 for (int pl = 0; pl < nplanes && ok; ++pl) {
-                    PIXIE_TR(tr, 0, ntr, 3);
                     ok = mbar_wait(&ctl->sempty[ss], sph ^ 1, abort_flag);
                     if (!ok) break;
-                    PIXIE_TR(tr, 0, ntr, 4);
                     if ((p.debug_flags & 2) && scount >= p.s_stages) { if (elect_one()) mbar_arrive(&ctl->sfull[ss]); }
                     else if (elect_one()) {
                         mbar_expect_tx(&ctl->sfull[ss], slab_bytes);
@@ -266,7 +192,6 @@ conv3d_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
                                     t.h0 * p.stride + P.dh0, (t.d0 + pl) * p.stride + P.dd0, t.nb);
                     }
                     ++scount;
-                    PIXIE_TR(tr, 0, ntr, 5);
                     if (++ss == p.s_stages) { ss = 0; sph ^= 1; }
                 }
             }
@@ -278,41 +203,28 @@ conv3d_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
         // elected lane. A single divergent thread costs ~25 scalar instructions per MMA (ncu: tensor pipe
         // 23 % busy, issue thread never waiting).
         int ws = 0, wph = 0, ss = 0, sph = 0, as = 0, aph = 0;
-        long long* mtr = (blockIdx.x == 0) ? p.trace : nullptr; int mntr = 0;
-        const int max_blk = min(3, 256 / block_n);                             // accumulator blocks one MMA may span
-        const uint32_t idesc1 = make_idesc_f16(128, (uint32_t)block_n), idesc2 = make_idesc_f16(128, (uint32_t)(2 * block_n)),
-                       idesc3 = make_idesc_f16(128, (uint32_t)(3 * block_n));
+        const int max_blk = min(3, 256 / p.block_n);                             // accumulator blocks one MMA may span
+        const uint32_t idesc1 = make_idesc_f16(128, (uint32_t)p.block_n), idesc2 = make_idesc_f16(128, (uint32_t)(2 * p.block_n)),
+                       idesc3 = make_idesc_f16(128, (uint32_t)(3 * p.block_n));
         const uint64_t desc_fixed = (make_sw128_desc(0, 1024) ^ p.desc_xor);   // everything but the start address
         const uint32_t desc_lo = (uint32_t)desc_fixed, desc_hi = (uint32_t)(desc_fixed >> 32);
+        const bool fast3 = (p.block_n == 64 || p.block_n == 128) && (p.TW == 16 || p.TW == 8);
         const uint32_t w_base0 = smem_u32(w_smem), s_base0 = smem_u32(s_smem);
-        const uint32_t kh_stride16 = (uint32_t)(TW * 128) >> 4;             // descriptor units of 16 B
-        const uint32_t tap_stride16 = (uint32_t)(block_n * 128) >> 4;
+        const uint32_t kh_stride16 = (uint32_t)(p.TW * 128) >> 4;             // descriptor units of 16 B
+        const uint32_t tap_stride16 = (uint32_t)(p.block_n * 128) >> 4;
         bool ok = true;
         for (int wi = blockIdx.x; wi < total_items && ok; wi += gridDim.x) {
-            if (lane == 0) PIXIE_TR(mtr, 1, mntr, 14);
-            const TileCoord t = decode_tile(p, wi, block_n, TW, TD);
-            if (lane == 0) PIXIE_TR(mtr, 1, mntr, 6);
+            const TileCoord t = decode_tile(p, wi);
             ok = mbar_wait(&ctl->tempty[as], aph ^ 1, abort_flag);
             if (!ok) break;
-            if (lane == 0) PIXIE_TR(mtr, 1, mntr, 7);
             tc_fence_after();
             for (int ph = t.ph_begin; ph < t.ph_end && ok; ++ph) {
-                const ConvPhase P = phases[ph];
+                const ConvPhase P = p.phases[ph];
                 const int n_kd = P.n_kd, n_kh = P.n_kh;
-                if (lane == 0) PIXIE_TR(mtr, 1, mntr, 1);
                 ok = mbar_wait(&ctl->wfull[ws], wph, abort_flag);
                 if (!ok) break;
-                if (lane == 0) PIXIE_TR(mtr, 1, mntr, 2);
                 const uint32_t w16 = (w_base0 + (uint32_t)(ws * p.w_stage_bytes)) >> 4;
                 const int nplanes = t.tde + n_kd - 1;
-                if (kBN != 0 && n_kh == 3 && n_kd == 3 && t.tde == TD) {
-                    const uint32_t acc_set = tmem_base + (uint32_t)(as * TD * block_n);
-                    const bool first = (ph == t.ph_begin), of = (p.debug_flags & 4) != 0;
-                    if constexpr (kBN != 0)
-                        ok = mma_phase_3x3<kBN ? kBN : 64, kTW ? kTW : 16, kTD ? kTD : 1>(ctl, p.s_stages, (uint32_t)p.s_stage_bytes, ss, sph, s_base0, w16,
-                                                                                  acc_set, first, desc_lo, desc_hi, of, abort_flag, mtr, mntr);
-                    if (lane == 0) PIXIE_TR(mtr, 1, mntr, 11);
-                } else
                 for (int pl = 0; pl < nplanes && ok; ++pl) {
                     ok = mbar_wait(&ctl->sfull[ss], sph, abort_flag);
                     if (!ok) break;
@@ -326,9 +238,23 @@ conv3d_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
                     const int nblk = d_max - d_min + 1, kd_hi = pl - d_min;
                     const bool fresh = (ph == t.ph_begin) && (d_max == pl);   // plane pl's accumulator is first touched here
                     if (elect_one()) {
-                        const uint32_t acc0 = tmem_base + (uint32_t)((as * TD + d_min) * block_n);
+                        const uint32_t acc0 = tmem_base + (uint32_t)((as * p.TD + d_min) * p.block_n);
                         const uint32_t wblk0 = (uint32_t)(n_kd - 1 - kd_hi);
                         const int nold0 = fresh ? nblk - 1 : nblk;
+                        if (n_kh == 3 && n_kd == 3 && nblk <= max_blk && fast3) {
+                            const uint32_t idA = nblk == 1 ? idesc1 : (nblk == 2 ? idesc2 : idesc3);
+                            const int nold = nblk - 1;
+                            const uint32_t id_old = nold == 1 ? idesc1 : idesc2;
+                            const uint32_t a_lo0 = desc_lo | (s16 & 0x3FFFu);
+                            const uint32_t b_lo0 = desc_lo | ((w16 + wblk0 * tap_stride16) & 0x3FFFu);
+                            if (p.block_n == 64) {
+                                if (p.TW == 16) issue_slab_3x3<64, 16>(acc0, a_lo0, b_lo0, desc_hi, idA, id_old, idesc1, nold, fresh);
+                                else issue_slab_3x3<64, 8>(acc0, a_lo0, b_lo0, desc_hi, idA, id_old, idesc1, nold, fresh);
+                            } else {
+                                if (p.TW == 16) issue_slab_3x3<128, 16>(acc0, a_lo0, b_lo0, desc_hi, idA, id_old, idesc1, nold, fresh);
+                                else issue_slab_3x3<128, 8>(acc0, a_lo0, b_lo0, desc_hi, idA, id_old, idesc1, nold, fresh);
+                            }
+                        } else
                         for (int kh = 0; kh < n_kh; ++kh) {
                             const uint32_t a16 = s16 + (uint32_t)kh * kh_stride16;
                             const uint32_t b16 = w16 + ((uint32_t)kh * (uint32_t)n_kd + wblk0) * tap_stride16;
@@ -341,11 +267,11 @@ conv3d_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
                                     const int cnt = min(max_blk, nold - b);
                                     const uint32_t idn = (cnt == 1) ? idesc1 : (cnt == 2 ? idesc2 : idesc3);
                                     const uint64_t db = desc_fixed | (uint64_t)((b16 + (uint32_t)b * tap_stride16 + 2u * k4) & 0x3FFFu);
-                                    umma_f16(acc0 + (uint32_t)(b * block_n), da, db, idn, 1u);
+                                    umma_f16(acc0 + (uint32_t)(b * p.block_n), da, db, idn, 1u);
                                 }
                                 if (split_new) {
                                     const uint64_t db = desc_fixed | (uint64_t)((b16 + (uint32_t)(nblk - 1) * tap_stride16 + 2u * k4) & 0x3FFFu);
-                                    umma_f16(acc0 + (uint32_t)((nblk - 1) * block_n), da, db, idesc1, 0u);
+                                    umma_f16(acc0 + (uint32_t)((nblk - 1) * p.block_n), da, db, idesc1, 0u);
                                 }
                             }
                         }
@@ -354,11 +280,9 @@ conv3d_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
                     if (++ss == p.s_stages) { ss = 0; sph ^= 1; }
                 }
                 if (elect_one()) umma_commit(&ctl->wempty[ws]);
-                if (lane == 0) PIXIE_TR(mtr, 1, mntr, 12);
                 if (++ws == p.w_stages) { ws = 0; wph ^= 1; }
             }
             if (elect_one()) umma_commit(&ctl->tfull[as]);            // accumulators complete
-            if (lane == 0) PIXIE_TR(mtr, 1, mntr, 13);
             __syncwarp();
             if (++as == p.acc_sets) { as = 0; aph ^= 1; }
         }
@@ -366,7 +290,7 @@ conv3d_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
         // ================================================================ epilogue (warps 2..5)
         const int q = warp & 3;                 // TMEM lane quarter this warp may access
         const int r = q * 32 + lane;            // accumulator row = voxel inside the plane tile
-        const int th = r / TW, tw = r % TW;
+        const int th = r / p.TW, tw = r % p.TW;
         int as = 0, aph = 0;
         bool ok = true;
         const long long DHW = (long long)p.D * p.H * p.W;
@@ -432,14 +356,11 @@ conv3d_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
             }
             __syncwarp();
         };
-        long long* etr = (blockIdx.x == 0 && warp == 2 && lane == 0) ? p.trace : nullptr; int entr = 0;
         const bool wide_ok = !p.out_planar && ((p.out_ld & 3) == 0) && ((p.out_c0 & 3) == 0);
         for (int wi = blockIdx.x; wi < total_items && ok; wi += gridDim.x) {
-            const TileCoord t = decode_tile(p, wi, block_n, TW, TD);
-            PIXIE_TR(etr, 2, entr, 8);
+            const TileCoord t = decode_tile(p, wi);
             ok = mbar_wait(&ctl->tfull[as], aph, abort_flag);
             if (!ok) break;
-            PIXIE_TR(etr, 2, entr, 9);
             tc_fence_after();
             if (do_stats && stats_nb != t.nb) {
                 if (stats_nb >= 0) flush_stats(stats_nb);
@@ -458,7 +379,7 @@ conv3d_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
                 const bool use_bias = first_split && p.bias != nullptr;
                 const bool use_res = row_ok && first_split && p.residual != nullptr;
                 const long long plane_ld = (long long)p.H * p.W * p.out_ld;
-                for (; c_wide + 32 <= block_n && t.n0 + c_wide + 32 <= p.Cout; c_wide += 32) {
+                for (; c_wide + 32 <= p.block_n && t.n0 + c_wide + 32 <= p.Cout; c_wide += 32) {
                     const int ch0 = t.n0 + c_wide;
                     float cs[32], cq[32];
 #pragma unroll
@@ -500,10 +421,10 @@ conv3d_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
                     };
                     for (int d = 0; d < t.tde; d += 2) {
                         const bool two = d + 1 < t.tde;                 // warp-uniform
-                        const uint32_t acc0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((as * TD + d) * block_n + c_wide);
+                        const uint32_t acc0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((as * p.TD + d) * p.block_n + c_wide);
                         uint32_t v0[32], v1[32];
                         tmem_ld32(acc0, v0);
-                        if (two) tmem_ld32(acc0 + (uint32_t)block_n, v1);
+                        if (two) tmem_ld32(acc0 + (uint32_t)p.block_n, v1);
                         const long long base0 = ((long long)t.nb * DHW + ((long long)(t.d0 + d) * p.H + hh) * p.W + ww) * p.out_ld + p.out_c0 + ch0;
                         float4 r0[8], r1[8];
                         if (use_res) {
@@ -539,10 +460,10 @@ conv3d_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
             for (int d = 0; d < t.tde && !(p.debug_flags & 1); ++d) {
                 const long long vox = ((long long)(t.d0 + d) * p.H + hh) * p.W + ww;   // inside batch item
                 const uint32_t acc = tmem_base + ((uint32_t)(q * 32) << 16) +
-                                     (uint32_t)((as * TD + d) * block_n);
+                                     (uint32_t)((as * p.TD + d) * p.block_n);
                 int c = c_wide;
                 // ---- generic path: 16 channels per step (ragged Cout, planar outputs, narrow tiles)
-                for (; c < block_n; c += 16) {
+                for (; c < p.block_n; c += 16) {
                     uint32_t v[16];
                     tmem_ld16(acc + (uint32_t)c, v);
                     tmem_ld_wait();
@@ -618,7 +539,6 @@ conv3d_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
             }
             tc_fence_before();
             __syncwarp();
-            PIXIE_TR(etr, 2, entr, 10);
             if (lane == 0) mbar_arrive(&ctl->tempty[as]);
             if (++as == p.acc_sets) { as = 0; aph ^= 1; }
         }
@@ -632,29 +552,6 @@ conv3d_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
         tc_fence_after();
         tmem_dealloc(tmem_base, tmem_cols);
     }
-}
-
-// Kernel variants: index 0 is the generic kernel, 1.. the (block_n, TW, TD) specialisations of the 3x3x3 fast path.
-using ConvKernelFn = void (*)(const ConvKernelParams);
-#define PIXIE_CONV_VARIANTS(X) \
-    X(64, 16, 1) X(64, 16, 2) X(64, 16, 3) X(64, 16, 4) X(64, 8, 1) X(64, 8, 2) X(64, 8, 3) X(64, 8, 4) \
-    X(128, 16, 1) X(128, 16, 2) X(128, 8, 1) X(128, 8, 2)
-constexpr int kNumConvVariants = 13;
-static ConvKernelFn conv_variant_kernel(int v) {
-    static const ConvKernelFn tab[kNumConvVariants] = {
-        conv3d_igemm_kernel<0, 0, 0>,
-#define X(bn, tw, td) conv3d_igemm_kernel<bn, tw, td>,
-        PIXIE_CONV_VARIANTS(X)
-#undef X
-    };
-    return tab[v];
-}
-static int conv_variant_index(int block_n, int TW, int TD) {
-    int i = 1;
-#define X(bn, tw, td) if (block_n == bn && TW == tw && TD == td) return i; ++i;
-    PIXIE_CONV_VARIANTS(X)
-#undef X
-    return 0;
 }
 
 // =====================================================================================  host side
@@ -827,7 +724,6 @@ int conv_plan_create(const ConvDesc& d, int* d_err_flag, ConvPlan& plan, char* e
     memset(&p, 0, sizeof(p));
     p.NB = d.NB; p.D = d.D; p.H = d.H; p.W = d.W; p.stride = d.stride;
     p.TW = (d.W >= 16) ? 16 : 8;
-    if (const char* e = getenv("PIXIE_CONV_TW")) p.TW = atoi(e);      // bring-up override
     p.TH = 128 / p.TW;
     p.Cout = d.Cout;
 
@@ -848,11 +744,9 @@ int conv_plan_create(const ConvDesc& d, int* d_err_flag, ConvPlan& plan, char* e
 
     // TD: accumulators per set
     int td = d.td ? d.td : std::min(4, 512 / (2 * bn));
-    int td_forced = d.td;
-    if (const char* e = getenv("PIXIE_CONV_TD")) { td = atoi(e); td_forced = td; }   // bring-up override
     td = std::max(1, std::min(td, d.D));
     if (!any3) td = std::min(td, 2);    // no plane re-use without kd taps: smaller tiles, more CTAs
-    if (!td_forced && td > 1) {
+    if (!d.td && td > 1) {
         // wave quantisation: a persistent grid of `sms` CTAs finishes in ceil(tiles/sms) rounds; prefer the
         // plane count with the better last-round fill (64^3: TD=4 -> 512 tiles = 3.46 rounds, TD=2 -> 6.92)
         int dev = 0, sms = 148;
@@ -891,13 +785,12 @@ int conv_plan_create(const ConvDesc& d, int* d_err_flag, ConvPlan& plan, char* e
     for (size_t i = 0; i < slots.size(); ++i) max_rows = std::max(max_rows, p.slab_rows[i]);
     p.w_stage_bytes = max_taps * bn * 128;
     p.s_stage_bytes = max_rows * 128;
-    // control block: barriers + phase table (when it fits 4 KB) + per-warp statistics rows; the 1 KB alignment slack is
-    // dropped when exactly that buys another slab stage (the kernel then verifies the base alignment itself)
+    // control block: barriers + per-warp statistics rows; the 1 KB alignment slack is dropped when exactly that buys
+    // another slab stage (the kernel then verifies the base alignment itself)
     plan.fused_stats = d.stats != nullptr && split == 1 && d.Cout <= kStatsMaxC && !d.out_planar;
-    p.phases_smem_bytes = p.n_phases <= kPhasesSmemMax ? (p.n_phases * (int)sizeof(ConvPhase) + 127) / 128 * 128 : 0;
     p.stats_ld = (d.Cout + 31) / 32 * 32;
     const int stats_bytes = plan.fused_stats ? 4 * 2 * p.stats_ld * 4 : 0;
-    const int ctl_core = kCtlBarrierBytes + p.phases_smem_bytes + stats_bytes;
+    const int ctl_core = kCtlBarrierBytes + stats_bytes;
     auto plan_stages = [&](int slack, int& ws, int& ss) {
         const int avail = 227 * 1024 - ctl_core - slack;
         ws = (2 * p.w_stage_bytes + 2 * p.s_stage_bytes <= avail) ? 2 : 1;
@@ -937,7 +830,6 @@ int conv_plan_create(const ConvDesc& d, int* d_err_flag, ConvPlan& plan, char* e
     p.stats_scalar = d.stats_scalar ? 1 : 0;
     p.desc_xor = 0;
     p.debug_flags = 0;
-    p.trace = nullptr;
     plan.out_bytes = d.out_planar ? (size_t)d.NB * d.Cout * d.D * d.H * d.W * 4
                                   : (size_t)d.NB * d.D * d.H * d.W * p.out_ld * 4;
 
@@ -946,12 +838,10 @@ int conv_plan_create(const ConvDesc& d, int* d_err_flag, ConvPlan& plan, char* e
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     plan.grid = std::min(items * split, sms);
 
-    plan.variant = getenv("PIXIE_CONV_GENERIC") ? 0 : conv_variant_index(p.block_n, p.TW, p.TD);   // env: bring-up A/B
     static bool attr_set = false;
     if (!attr_set) {
-        for (int v = 0; v < kNumConvVariants; ++v)
-            if (cudaFuncSetAttribute(conv_variant_kernel(v), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
-                return fail("cudaFuncSetAttribute(max dynamic smem)");
+        if (cudaFuncSetAttribute(conv3d_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+            return fail("cudaFuncSetAttribute(max dynamic smem)");
         attr_set = true;
     }
     return 0;
@@ -968,7 +858,7 @@ int conv_plan_launch(const ConvPlan& plan, cudaStream_t stream) {
         // cleared when out_ld > Cout, so callers with sliced outputs must not use split-K.
         cudaMemsetAsync(plan.p.out, 0, plan.out_bytes, stream);
     }
-    conv_variant_kernel(plan.variant)<<<plan.grid, kConvThreads, plan.smem_bytes, stream>>>(plan.p);
+    conv3d_igemm_kernel<<<plan.grid, kConvThreads, plan.smem_bytes, stream>>>(plan.p);
     return (int)cudaGetLastError();
 }
 

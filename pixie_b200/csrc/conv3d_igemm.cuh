@@ -75,12 +75,10 @@ struct ConvKernelParams {
     double* stats;           // optional [NB][Cout][2] = (sum, sum of squares) of the outputs over voxels,
                              // accumulated by the epilogue (fused LayerNorm/GroupNorm statistics); or nullptr
     int stats_ld;            // floats per statistics row in shared memory (Cout rounded up to 32)
-    int phases_smem_bytes;   // size of the phase table copy in shared memory (0: read phases from global)
     int smem_slack;          // bytes reserved for aligning the dynamic smem base to 1 KB (0: the base must already be aligned)
     int stats_scalar;        // 1: only the per-item totals are wanted; they land in channel 0's slot (LayerNorm consumers)
     int* err_flag;           // device int, set non-zero on pipeline timeout
     uint64_t desc_xor;       // bring-up only: xor into every smem matrix descriptor (0 in product use)
-    long long* trace;        // bring-up only: per-role clock64 event log of CTA 0 ([4 roles][4096] entries), or nullptr
     int debug_flags;         // bring-up only, timing experiments (results are WRONG when set): 1 = epilogue skips its body,
                              // 2 = producer stops issuing TMA once every stage was filled
 };
@@ -133,7 +131,6 @@ struct ConvPlan {
     ConvPhase* d_phases = nullptr;
     int grid = 0;
     int smem_bytes = 0;
-    int variant = 0;           // kernel instantiation (0 = generic)
     bool needs_zero = false;   // out must be zeroed before launch (atomic_out)
     bool fused_stats = false;  // the epilogue accumulates ConvDesc::stats (needs split_k == 1, Cout <= 256)
     size_t out_bytes = 0;

@@ -144,12 +144,6 @@ int main(int argc, char** argv) {
         }
         plan.p.desc_xor = hi_xor;
         if (getenv("CONV_DEBUG")) plan.p.debug_flags = atoi(getenv("CONV_DEBUG"));
-        long long* d_trace = nullptr;
-        if (getenv("CONV_TRACE") && c.timing) {
-            CK(cudaMalloc(&d_trace, 4 * 4096 * sizeof(long long)));
-            CK(cudaMemset(d_trace, 0, 4 * 4096 * sizeof(long long)));
-            plan.p.trace = d_trace;
-        }
         printf("[%s] grid=%d smem=%d bn=%d TD=%d TW=%d TH=%d acc_sets=%d w_stages=%d s_stages=%d phases=%d split=%d\n",
                c.name.c_str(), plan.grid, plan.smem_bytes, plan.p.block_n, plan.p.TD, plan.p.TW, plan.p.TH,
                plan.p.acc_sets, plan.p.w_stages, plan.p.s_stages, plan.p.n_phases, plan.p.split_k);
@@ -167,33 +161,31 @@ int main(int argc, char** argv) {
             continue;
         }
 
-        if (d_trace) {
-            // one traced launch: dump CTA 0's event log (role, code, cycle relative to the first event)
-            conv_plan_launch(plan, 0);
-            CK(cudaDeviceSynchronize());
-            std::vector<long long> h_tr(4 * 4096);
-            CK(cudaMemcpy(h_tr.data(), d_trace, h_tr.size() * sizeof(long long), cudaMemcpyDeviceToHost));
-            long long t0 = -1;
-            for (long long v : h_tr) if (v && (t0 < 0 || (v >> 8) < t0)) t0 = v >> 8;
-            FILE* f = fopen(getenv("CONV_TRACE"), "w");
-            for (int r = 0; r < 4; ++r)
-                for (int i = 0; i < 4096 && h_tr[r * 4096 + i]; ++i)
-                    fprintf(f, "%d %d %lld\n", r, (int)(h_tr[r * 4096 + i] & 0xFF), (h_tr[r * 4096 + i] >> 8) - t0);
-            fclose(f);
-            plan.p.trace = nullptr;
-            cudaFree(d_trace);
-        }
         if (c.timing) {
             cudaEvent_t e0, e1;
             cudaEventCreate(&e0); cudaEventCreate(&e1);
             for (int i = 0; i < 3; ++i) conv_plan_launch(plan, 0);
-            cudaEventRecord(e0);
             const int iters = 20;
-            for (int i = 0; i < iters; ++i) conv_plan_launch(plan, 0);
-            cudaEventRecord(e1);
-            CK(cudaEventSynchronize(e1));
             float ms = 0;
-            cudaEventElapsedTime(&ms, e0, e1);
+            if (getenv("CONV_TEST_COLD")) {
+                // cold launches: a 512 MB memset (evicts L2 and the instruction caches' backing lines) before every timed launch
+                static void* scrub = nullptr;
+                if (!scrub) CK(cudaMalloc(&scrub, 512u << 20));
+                for (int i = 0; i < iters; ++i) {
+                    CK(cudaMemsetAsync(scrub, i, 512u << 20, 0));
+                    cudaEventRecord(e0);
+                    conv_plan_launch(plan, 0);
+                    cudaEventRecord(e1);
+                    CK(cudaEventSynchronize(e1));
+                    float t = 0; cudaEventElapsedTime(&t, e0, e1); ms += t;
+                }
+            } else {
+                cudaEventRecord(e0);
+                for (int i = 0; i < iters; ++i) conv_plan_launch(plan, 0);
+                cudaEventRecord(e1);
+                CK(cudaEventSynchronize(e1));
+                cudaEventElapsedTime(&ms, e0, e1);
+            }
             ms /= iters;
             double flops = 2.0 * vox_out * c.Cout * (double)conv_k_total(d);
             printf("[%s] TIME %.3f ms  %.1f TFLOP/s (padded-K flops)  [bn=%d TW=%d TD=%d w_stages=%d s_stages=%d split=%d smem=%d]\n", c.name.c_str(), ms, flops / ms * 1e-9,
