@@ -634,6 +634,46 @@ static void substep(sim_t* s, double dt_d) {
 void mpmref_step(sim_t* s, int n_substeps, double dt) {
     for (int i = 0; i < n_substeps; ++i) substep(s, dt);
 }
+/* ---- split substep for slab-decomposed runs (test double of pixie_mpm_substep_scatter / _finish; the reference has
+ *      no multi-GPU path). The caller owns the zero-invariant: planes outside the finished range
+ *      keep whatever was scattered into them. */
+void mpmref_set_active(sim_t* s, int n_active) { s->n = n_active; }
+void mpmref_scatter(sim_t* s, double dt_d) {
+    const real dt = (real)dt_d;
+    const float time = (float)s->time;
+    for (int p = 0; p < s->n; ++p) { particle_bcs(s, p, time, dt); compute_stress(s, p, dt); }
+    for (int p = 0; p < s->n; ++p) p2g_particle(s, p, dt);
+}
+void mpmref_finish(sim_t* s, double dt_d, int x_begin, int x_end) {
+    const real dt = (real)dt_d;
+    const float time = (float)s->time;
+    const size_t plane = (size_t)s->n_grid * s->n_grid;
+    for (size_t i = (size_t)x_begin * plane; i < (size_t)x_end * plane; ++i) grid_node(s, i, time, dt);
+    for (int k = 0; k < s->n_bc; ++k) {
+        bc_t* bc = &s->bcs[k];
+        if (bc->kind == BC_CUBOID && s->time >= (double)bc->start_time && s->time < (double)bc->end_time)
+            for (int a = 0; a < 3; ++a) bc->point[a] = (real)((double)bc->point[a] + dt_d * (double)bc->velocity[a]);
+    }
+    for (int p = 0; p < s->n; ++p) g2p_particle(s, p, dt);
+    memset(s->grid_m + (size_t)x_begin * plane, 0, (size_t)(x_end - x_begin) * plane * sizeof(real));
+    memset(s->grid_v_in + 3 * (size_t)x_begin * plane, 0, 3 * (size_t)(x_end - x_begin) * plane * sizeof(real));
+    s->time = s->time + dt_d;
+}
+/* planes [a, b) of the scatter target as {mv.x, mv.y, mv.z, m} per node (the CUDA grid layout) */
+void mpmref_planes_get(sim_t* s, int a, int b, double* out) {
+    const size_t plane = (size_t)s->n_grid * s->n_grid;
+    for (size_t i = (size_t)a * plane, k = 0; i < (size_t)b * plane; ++i, ++k) {
+        out[4 * k] = s->grid_v_in[3 * i]; out[4 * k + 1] = s->grid_v_in[3 * i + 1]; out[4 * k + 2] = s->grid_v_in[3 * i + 2];
+        out[4 * k + 3] = s->grid_m[i];
+    }
+}
+void mpmref_planes_add(sim_t* s, int a, int b, const double* in) {
+    const size_t plane = (size_t)s->n_grid * s->n_grid;
+    for (size_t i = (size_t)a * plane, k = 0; i < (size_t)b * plane; ++i, ++k) {
+        s->grid_v_in[3 * i] += (real)in[4 * k]; s->grid_v_in[3 * i + 1] += (real)in[4 * k + 1]; s->grid_v_in[3 * i + 2] += (real)in[4 * k + 2];
+        s->grid_m[i] += (real)in[4 * k + 3];
+    }
+}
 int mpmref_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -52,6 +52,11 @@ def _lib(precision: str) -> C.CDLL:
     lib.mpmref_stress_of_F.argtypes = [C.c_void_p, C.c_int]
     lib.mpmref_step.argtypes = [C.c_void_p, C.c_int, C.c_double]
     lib.mpmref_num_threads.restype = C.c_int
+    lib.mpmref_set_active.argtypes = [C.c_void_p, C.c_int]
+    lib.mpmref_scatter.argtypes = [C.c_void_p, C.c_double]
+    lib.mpmref_finish.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_int]
+    lib.mpmref_planes_get.argtypes = [C.c_void_p, C.c_int, C.c_int, D]
+    lib.mpmref_planes_add.argtypes = [C.c_void_p, C.c_int, C.c_int, D]
     lib.mpmref_real_size.restype = C.c_int
     _libs[precision] = lib
     return lib
@@ -81,6 +86,7 @@ class MpmRef:
     def __init__(self, n: int, n_grid: int, grid_lim: float, precision: str = "f32"):
         self.lib = _lib(precision)
         self.n, self.n_grid, self.grid_lim, self.precision = n, n_grid, grid_lim, precision
+        self.capacity = n
         self.h = C.c_void_p(self.lib.mpmref_create(n, n_grid, float(grid_lim)))
         self.params = dict(g=(0.0, 0.0, 0.0), rpic_damping=0.0, grid_v_damping_scale=1.1, alpha=friction_alpha(25.0),
                            hardening=0.0, xi=0.0, plastic_viscosity=0.0, softening=0.1, update_cov_with_F=0,
@@ -158,6 +164,28 @@ class MpmRef:
 
     def step(self, n_substeps: int, dt: float):
         self.lib.mpmref_step(self.h, int(n_substeps), float(dt))
+
+    # ---- split substep (test double of pixie_mpm_substep_scatter / _finish for the slab-decomposition tests)
+    def set_active(self, n_active: int):
+        assert 0 <= n_active <= self.capacity
+        self.n = int(n_active)
+        self.lib.mpmref_set_active(self.h, self.n)
+
+    def scatter(self, dt: float):
+        self.lib.mpmref_scatter(self.h, float(dt))
+
+    def finish(self, dt: float, x_begin: int, x_end: int):
+        self.lib.mpmref_finish(self.h, float(dt), int(x_begin), int(x_end))
+
+    def planes_get(self, a: int, b: int) -> np.ndarray:
+        out = np.zeros((b - a) * self.n_grid * self.n_grid * 4)
+        self.lib.mpmref_planes_get(self.h, int(a), int(b), _dp(out))
+        return out
+
+    def planes_add(self, a: int, b: int, data: np.ndarray):
+        d = np.ascontiguousarray(data, dtype=np.float64).reshape(-1)
+        assert d.size == (b - a) * self.n_grid * self.n_grid * 4
+        self.lib.mpmref_planes_add(self.h, int(a), int(b), _dp(d))
 
     def num_threads(self) -> int:
         return int(self.lib.mpmref_num_threads())
