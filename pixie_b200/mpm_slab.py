@@ -54,6 +54,7 @@ class CudaSlabBackend:
             self.grid = torch.zeros((n, n * n * 4), dtype=torch.float32, device=self.device)
         self._check(self.lib.pixie_mpm_bind_grid(solver._handle, C.c_void_p(self.grid.data_ptr())))
         self._active = -1
+        self._slab = None
         self.set_active(n_active)
 
     def _check(self, rc: int):
@@ -70,12 +71,18 @@ class CudaSlabBackend:
 
     def finish(self, dt: float, lo: int, hi: int):
         with torch.cuda.device(self.device):
-            self._check(self.lib.pixie_mpm_set_slab(self.solver._handle, int(lo), int(hi)))
+            if (lo, hi) != self._slab:
+                self._check(self.lib.pixie_mpm_set_slab(self.solver._handle, int(lo), int(hi)))
+                self._slab = (lo, hi)
             self._check(self.lib.pixie_mpm_substep_finish(self.solver._handle, float(dt), self._stream()))
 
     # -- grid planes {mv.xyz, m}
     def planes(self, a: int, b: int) -> torch.Tensor:
         return self.grid[a:b].clone()
+
+    def planes_view(self, a: int, b: int) -> torch.Tensor:
+        """No copy: x is the slowest grid dimension, so a plane range is one contiguous block (valid until the next add)."""
+        return self.grid[a:b]
 
     def planes_add(self, a: int, b: int, t: torch.Tensor):
         self.grid[a:b] += t.to(self.grid.dtype)
@@ -103,6 +110,32 @@ class CudaSlabBackend:
             t = self.get(name)
             cols.append(t.view(torch.float32) if t.dtype == torch.int32 else t)
         return torch.cat(cols, dim=1)
+
+    def records_at(self, index: torch.Tensor) -> torch.Tensor:
+        """Records of the particles `index` only (migration touches a few thousand of them, not the whole slab)."""
+        cols = []
+        for name, w in self.FIELDS:
+            t = self.get(name)[index]
+            cols.append(t.view(torch.float32) if t.dtype == torch.int32 else t)
+        return torch.cat(cols, dim=1)
+
+    def compact_and_append(self, keep_index: torch.Tensor, arrivals: Optional[torch.Tensor]):
+        """Live prefix <- particles `keep_index` (in order) followed by the `arrivals` records."""
+        n_keep = int(keep_index.shape[0])
+        n_new = 0 if arrivals is None else int(arrivals.shape[0])
+        old = self._active
+        if n_keep + n_new > self.capacity:
+            raise RuntimeError(f"slab would hold {n_keep + n_new} particles but was created with capacity {self.capacity}")
+        c = 0
+        for name, w in self.FIELDS:
+            full = self.solver._t[name].view(self.capacity, w)
+            if n_keep != old:
+                full[:n_keep] = full[:old][keep_index]
+            if n_new:
+                src = arrivals[:, c:c + w].contiguous()
+                full[n_keep:n_keep + n_new] = src.view(torch.int32) if full.dtype == torch.int32 else src
+            c += w
+        self.set_active(n_keep + n_new)
 
     def set_records(self, rec: torch.Tensor):
         n = rec.shape[0]
@@ -150,6 +183,13 @@ class SlabRank:
         right = self.b.planes(*self.right_ov) if self.has_right else None
         return left, right
 
+    def snapshot_views(self):
+        """Same without copies, for drivers that finish sending before they accumulate (backends without views copy)."""
+        pv = getattr(self.b, "planes_view", self.b.planes)
+        left = pv(*self.left_ov) if self.has_left else None
+        right = pv(*self.right_ov) if self.has_right else None
+        return left, right
+
     def accumulate(self, from_left, from_right):
         if self.has_left:
             self.b.planes_add(self.left_ov[0], self.left_ov[1], from_left)
@@ -165,23 +205,32 @@ class SlabRank:
 
     # -- migration phases
     def migrate_collect(self):
-        """Splits the live particles into (stay, to_left, to_right) records; ids ride along as a last column pair."""
-        rec = self.b.records()
+        """Splits the live particles into stay / to_left / to_right. Returns (stay_index, (rec, ids) left, (rec, ids) right)."""
         x = self.b.get("X")[:, 0]
         # base plane exactly as the kernels compute it: float32 product, truncation toward zero (mpm_utils.py:344-346)
         base = (x.to(torch.float32) * torch.tensor(self.b.inv_dx, dtype=torch.float32, device=x.device) - 0.5).to(torch.int32)
         go_left = (base < self.x0) if self.has_left else torch.zeros_like(base, dtype=torch.bool)
         go_right = (base >= self.x1) if self.has_right else torch.zeros_like(base, dtype=torch.bool)
-        stay = ~(go_left | go_right)
-        ids = self.ids.to(rec.device)
-        pack = lambda m: (rec[m], ids[m])
-        return pack(stay), pack(go_left), pack(go_right)
+        stay_idx = torch.nonzero(~(go_left | go_right)).flatten()
+        il, ir = torch.nonzero(go_left).flatten(), torch.nonzero(go_right).flatten()
+        ids = self.ids.to(x.device)
+        if hasattr(self.b, "records_at"):
+            pack = lambda i: (self.b.records_at(i), ids[i])
+        else:
+            rec = self.b.records()
+            pack = lambda i: (rec[i], ids[i])
+        return stay_idx, pack(il), pack(ir)
 
-    def migrate_apply(self, stay, from_left, from_right):
-        recs = [stay[0]] + [p[0] for p in (from_left, from_right) if p is not None and p[0].shape[0] > 0]
-        ids = [stay[1]] + [p[1] for p in (from_left, from_right) if p is not None and p[0].shape[0] > 0]
-        self.b.set_records(torch.cat(recs, dim=0))
-        self.ids = torch.cat(ids, dim=0)
+    def migrate_apply(self, stay_idx, from_left, from_right):
+        ids = self.ids.to(stay_idx.device)
+        arrivals = [p for p in (from_left, from_right) if p is not None and p[0].shape[0] > 0]
+        new_rec = torch.cat([p[0] for p in arrivals], dim=0) if arrivals else None
+        if hasattr(self.b, "compact_and_append"):
+            self.b.compact_and_append(stay_idx, new_rec)
+        else:
+            rec = self.b.records()[stay_idx]
+            self.b.set_records(rec if new_rec is None else torch.cat([rec, new_rec.to(rec.dtype)], dim=0))
+        self.ids = torch.cat([ids[stay_idx]] + [p[1].to(ids.device) for p in arrivals], dim=0)
 
 
 class LocalSlabCluster:
@@ -223,16 +272,18 @@ class DistSlabDriver:
     def __init__(self, rank_obj: SlabRank, group=None):
         import torch.distributed as dist
         self.r, self.dist, self.group = rank_obj, dist, group
+        self._recv = None
 
-    def _swap(self, to_left: Optional[torch.Tensor], to_right: Optional[torch.Tensor], like_left=None, like_right=None):
-        """Symmetric neighbour exchange of same-shape tensors."""
+    def _swap(self, to_left: Optional[torch.Tensor], to_right: Optional[torch.Tensor], like_left=None, like_right=None, reuse=False):
+        """Symmetric neighbour exchange. `like_*` give the shape of what is received (default: what is sent); with
+        `reuse` they ARE the receive buffers."""
         dist, r = self.dist, self.r
         ops, from_left, from_right = [], None, None
         if r.has_left:
-            from_left = torch.empty_like(to_left if like_left is None else like_left)
+            from_left = like_left if reuse else torch.empty_like(to_left if like_left is None else like_left)
             ops += [dist.P2POp(dist.isend, to_left.contiguous(), r.rank - 1, self.group), dist.P2POp(dist.irecv, from_left, r.rank - 1, self.group)]
         if r.has_right:
-            from_right = torch.empty_like(to_right if like_right is None else like_right)
+            from_right = like_right if reuse else torch.empty_like(to_right if like_right is None else like_right)
             ops += [dist.P2POp(dist.isend, to_right.contiguous(), r.rank + 1, self.group), dist.P2POp(dist.irecv, from_right, r.rank + 1, self.group)]
         if ops:
             for w in dist.batch_isend_irecv(ops):
@@ -257,8 +308,10 @@ class DistSlabDriver:
     def substep(self, dt: float):
         r = self.r
         r.scatter(dt)
-        left, right = r.snapshot()
-        from_left, from_right = self._swap(left, right)
+        left, right = r.snapshot_views()
+        if self._recv is None:          # overlap-plane receive buffers, allocated once
+            self._recv = (torch.empty_like(left) if r.has_left else None, torch.empty_like(right) if r.has_right else None)
+        from_left, from_right = self._swap(left, right, self._recv[0], self._recv[1], reuse=True)
         r.accumulate(from_left, from_right)
         r.finish(dt)
         if r.due_for_migration():
