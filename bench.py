@@ -293,7 +293,10 @@ def run_ours(args, emit):
         ach = conv_fl / (conv_ms * 1e-3) * 1e-12
         roof = {"kernel": "conv3d_igemm_kernel (tcgen05 implicit GEMM), all convolutions of seg+reg", "bound": "tensor",
                 "achieved": ach, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": ach / pk["tensor"], "peak_burst": pk["tensor_burst"],
-                "peak_source": pk["src"] + ", sustained bf16", "traffic": None,
+                "peak_source": pk["src"] + ", sustained bf16",
+                # dram__bytes_read.sum + dram__bytes_write.sum of ONE dominant launch (64->64 3x3x3 @ 64^3, 58.0 GFLOP, algorithmic
+                # bytes 100.9 MB) from the committed ncu --set full capture (profiles/r01_final_summary.md section 3)
+                "traffic": 48.6e6, "traffic_launch": "64->64 3x3x3 conv @ 64^3 (fp16 pass): algorithmic 100.9e6 B, ncu dram 48.6e6 B",
                 "note": "achieved = algorithmic FLOPs (2*MACs of the reference graph) / sum of conv launch times from CUDA events; "
                         + ("fp16x3 executes 3 tensor-core passes per algorithmic FLOP" if args.precision == "fp16x3" else "1 tensor-core pass")}
         breakdown = {k: {"launches": v[0], "ms": round(v[1], 4)} for k, v in by.items()}
