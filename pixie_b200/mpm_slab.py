@@ -19,7 +19,7 @@ Restrictions (checked): slabs must be at least 2 + 2*slack planes wide; boundary
 (impulses, velocity translation / rotation) are not migrated and are rejected.
 
 The orchestration is backend-agnostic: `CudaSlabBackend` drives the C ABI; the CPU tests drive the same orchestration
-with a test double built on the oracle (tests/slab_backends.py) over gloo.
+with a CPU test double (tests/slab_backends.py), in one process and over gloo.
 """
 from __future__ import annotations
 
