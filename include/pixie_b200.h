@@ -79,6 +79,24 @@ int pixie_unet_profile(pixie_unet_t h, const void* feat_ndhwc_f16_dev, int batch
  * continuous channels followed by the one-hot of argmax(seg_logits). All pointers device, planar NCDHW. */
 int pixie_pack_predictions(const float* seg_logits_dev, const float* cont_dev, float* out_dev, int batch,
                            int64_t voxels, int n_classes, void* stream);
+/* ---- material field -> particles. All array pointers are DEVICE pointers unless marked host.
+ * pixie_field_extract: pixie/voxel/map_pred_to_coords.py:41-75 (unscale_prediction: clip to [-1,1], 10**log for density
+ * and E, linear nu) + :198-245 (argmax material id, confidence = max class value, np.linspace voxel centres, mask > 0
+ * compaction in C order). pred = packed (3 + n_classes, D, D, D) fp32, mask = (D, D, D) fp32. ranges (host) =
+ * {density_min, density_max, E_min, E_max, nu_min, nu_max} of normalization_ranges.yaml. Outputs need room for D^3
+ * entries; *count_host = number of occupied voxels. Synchronises `stream`. */
+int pixie_field_extract(const float* pred_dev, int n_classes, const float* mask_dev, int D, const double ranges_host[6],
+                        const double min_bounds_host[3], const double max_bounds_host[3], float* pos_dev, float* density_dev,
+                        float* E_dev, float* nu_dev, int* material_dev, float* conf_dev, int* count_host, void* stream);
+/* pixie_knn_assign: PG/material_field.py:228-293 (perform_knn_smoothing) with assign_from_neighbors (:57-86): exact k nearest
+ * material points per query (k <= 16), continuous properties = mean (np.mean order) or inverse-distance weighted mean,
+ * categorical = mode (Counter.most_common / weighted bincount); queries farther than nn_distance_threshold from their nearest
+ * point receive the defaults {density, E, nu, conf}, default_material, default_part. *n_too_far_host counts them. */
+int pixie_knn_assign(const float* query_dev, int n_query, const float* pos_dev, const float* density_dev, const float* E_dev,
+                     const float* nu_dev, const int* material_dev, const int* part_dev, const float* conf_dev, int n_points, int k,
+                     float nn_distance_threshold, int weighted, const float defaults_host[4], int default_material, int default_part,
+                     float* out_density_dev, float* out_E_dev, float* out_nu_dev, int* out_material_dev, int* out_part_dev,
+                     float* out_conf_dev, int* n_too_far_host, void* stream);
 /* Number of kernel launches one forward() issues (for gpu_launches accounting) and algorithmic
  * FLOPs of one forward at batch 1 (2 * MACs of every Conv3d/Conv1d of the reference graph). */
 int pixie_unet_launch_count(pixie_unet_t h);
@@ -182,8 +200,8 @@ int pixie_mpm_compute_cov_from_F(pixie_mpm_t h, void* stream);             /* mp
 int pixie_mpm_compute_R_from_F(pixie_mpm_t h, void* stream);               /* mpm_utils.py:556-580 */
 /* apply_additional_params for a LIST of boxes in one launch (mpm_utils.py:591-610; the reference
  * launches it once per box, material_field.py:343-363). boxes: [n_boxes][10] =
- * point xyz, size xyz, E, nu, density, material(as float). */
-int pixie_mpm_apply_additional_params(pixie_mpm_t h, const float* boxes_host, int n_boxes, void* stream);
+ * point xyz, size xyz, E, nu, density, material(as float); the array may live on the host or on the device. */
+int pixie_mpm_apply_additional_params(pixie_mpm_t h, const float* boxes, int n_boxes, void* stream);
 /* selection_* mask kernels (mpm_utils.py:613-663): writes int32 mask_dev[n]. */
 int pixie_mpm_select_box(pixie_mpm_t h, const float point[3], const float size[3], int* mask_dev, void* stream);
 int pixie_mpm_select_cylinder(pixie_mpm_t h, const float point[3], const float normal[3],

@@ -83,6 +83,11 @@ _SIGNATURES = {
     "pixie_mpm_select_box": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_void_p, C.c_void_p]),
     "pixie_mpm_select_cylinder": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_float, C.c_float, C.c_void_p, C.c_void_p]),
     "pixie_mpm_sync": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "pixie_field_extract": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.c_void_p]),
+    "pixie_knn_assign": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                   C.c_int, C.c_float, C.c_int, C.POINTER(C.c_float), C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.c_void_p]),
     "pixie_mpm_bind_grid": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pixie_mpm_set_slab": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "pixie_mpm_set_active_count": (C.c_int, [C.c_void_p, C.c_int]),

@@ -3,6 +3,7 @@
 #include "mpm.cuh"
 #include "unet.cuh"
 #include "unet_kernels.cuh"
+#include "field_transfer.cuh"
 
 #include <string>
 
@@ -72,6 +73,29 @@ int pixie_unet_profile(pixie_unet_t h, const void* feat, int batch, float* out, 
     const int n = pixie::unet_profile(h->u, feat, batch, out, (cudaStream_t)stream, ms, kinds, flops, cap);
     if (n < 0) set_err(pixie::unet_error(h->u));
     return n;
+}
+int pixie_field_extract(const float* pred, int n_classes, const float* mask, int D, const double ranges[6], const double bmin[3], const double bmax[3],
+                        float* pos, float* density, float* E, float* nu, int* material, float* conf, int* count_host, void* stream) {
+    if (!pred || !mask || !ranges || !bmin || !bmax || !pos || !density || !E || !nu || !material || !conf || !count_host) return set_err("null argument");
+    if (D < 2 || n_classes < 1) return set_err("field_extract: need D >= 2 and at least one class channel");
+    if (require_device()) return 1;
+    if (pixie::field_extract(pred, n_classes, mask, D, ranges, bmin, bmax, pos, density, E, nu, material, conf, count_host, (cudaStream_t)stream))
+        return set_err("field_extract failed");
+    return 0;
+}
+int pixie_knn_assign(const float* query, int nq, const float* pos, const float* density, const float* E, const float* nu, const int* material,
+                     const int* part, const float* conf, int m, int k, float threshold, int weighted, const float defaults[4], int def_material,
+                     int def_part, float* o_density, float* o_E, float* o_nu, int* o_material, int* o_part, float* o_conf, int* n_too_far_host,
+                     void* stream) {
+    if (!query || !pos || !density || !E || !nu || !material || !part || !conf || !defaults || !o_density || !o_E || !o_nu || !o_material ||
+        !o_part || !o_conf || !n_too_far_host) return set_err("null argument");
+    if (k < 1 || k > 16) return set_err("knn_assign: k must be in [1, 16]");
+    if (m < 1) return set_err("knn_assign: empty material point cloud");
+    if (require_device()) return 1;
+    if (pixie::knn_assign(query, nq, pos, density, E, nu, material, part, conf, m, k, threshold, weighted, defaults, def_material, def_part,
+                          o_density, o_E, o_nu, o_material, o_part, o_conf, n_too_far_host, (cudaStream_t)stream))
+        return set_err("knn_assign failed");
+    return 0;
 }
 int pixie_pack_predictions(const float* seg_logits_dev, const float* cont_dev, float* out_dev, int batch, int64_t voxels, int n_classes, void* stream) {
     if (!seg_logits_dev || !cont_dev || !out_dev) return set_err("null argument");

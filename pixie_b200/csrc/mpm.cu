@@ -989,7 +989,7 @@ int mpm_apply_additional_params(Mpm* m, const float* boxes_host, int n_boxes, cu
     if (mpm_sync(m, st)) return 1;
     float* d = nullptr;
     if (cudaMalloc(&d, (size_t)n_boxes * 10 * 4) != cudaSuccess) { m->error = "cudaMalloc failed"; return 1; }
-    cudaMemcpyAsync(d, boxes_host, (size_t)n_boxes * 10 * 4, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(d, boxes_host, (size_t)n_boxes * 10 * 4, cudaMemcpyDefault, st);    // host or device source (UVA)
     const DevState s = make_state(m);
     mpm_additional_params_kernel<<<(m->n + 127) / 128, 128, 0, st>>>(s, d, n_boxes);
     cudaStreamSynchronize(st);

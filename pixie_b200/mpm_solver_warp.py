@@ -301,6 +301,14 @@ class MPM_Simulator_WARP:
                                                                  self._stream()))
             _lib.check(lib.pixie_mpm_compute_mass(self._handle, self._stream()))
 
+    def _apply_additional_params_boxes(self, boxes: torch.Tensor):
+        """`additional_material_params` as an (n_boxes, 10) float32 device tensor (point, size, E, nu, density, material):
+        the per-box `apply_additional_params` launches (:436-452) + the mass update (:454-463) without a Python dict per box."""
+        lib = _lib.load()
+        b = boxes.detach().to(self._device, torch.float32).contiguous()
+        _lib.check(lib.pixie_mpm_apply_additional_params(self._handle, C.c_void_p(b.data_ptr()), int(b.shape[0]), self._stream()))
+        _lib.check(lib.pixie_mpm_compute_mass(self._handle, self._stream()))
+
     def finalize_mu_lam(self, device="cuda:0"):
         _lib.check(_lib.load().pixie_mpm_compute_mu_lam(self._handle, self._stream()))
 
