@@ -277,7 +277,22 @@ def run_ours(args, emit):
         solver.p2g2p_n(SUB, 1e-4)
         x_out_host.copy_(solver.export_particle_x_to_torch(), non_blocking=True)
         torch.cuda.current_stream().synchronize()
-    ms_e2e_unet = timed(e2e_unet, args.steps, args.warmup)
+    # K scenes through the pipelined host API: scene i+1's H2D overlaps scene i's networks; every scene's H2D and D2H is inside the
+    # timed region, which is bracketed like the others (barrier + synchronize, CUDA events, max over ranks). The 268 MB input
+    # grid is larger than L2, so there is no flush between the scenes of one pipelined run.
+    def e2e_unet_pipelined(k):
+        pred.predict_packed_host_stream([feat_host] * k, [packed_host] * k)
+    for _ in range(max(1, args.warmup // 2)):
+        e2e_unet_pipelined(2)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); e2e_unet_pipelined(args.steps); e1.record()
+    barrier()
+    tt = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms_e2e_unet = float(tt.item())
+    ms_e2e_unet_serial = timed(e2e_unet, args.steps, args.warmup)
     ms_e2e_mpm = timed(e2e_mpm, args.steps, args.warmup, prep=mpm_prep)
     h2d = feat_host.numel() * 2 + sum(t.numel() * 4 for t in host_scene.values())
     d2h = packed_host.numel() * 4 + x_out_host.numel() * 4
@@ -346,7 +361,9 @@ def run_ours(args, emit):
         "cpu_baseline": cpu, "parity": parity,
         "e2e": {"value": world * G ** 3 * K / (ms_e2e_unet * 1e-3), "unit": "voxels/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "mpm_value": world * n * SUB * K / (ms_e2e_mpm * 1e-3), "mpm_unit": "particle-steps/s",
-                "ms_per_step": (ms_e2e_unet + ms_e2e_mpm) / K},
+                "ms_per_step": (ms_e2e_unet + ms_e2e_mpm) / K,
+                "api": "MaterialFieldPredictor.predict_packed_host_stream (H2D of scene i+1 overlaps the networks of scene i) + MPM_Simulator_WARP.p2g2p_n",
+                "unpipelined_value": world * G ** 3 * K / (ms_e2e_unet_serial * 1e-3)},
         "gpu_launches": n_launch, "clocks": clocks,
     }
     emit(json.dumps(line))

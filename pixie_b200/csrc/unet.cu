@@ -71,15 +71,16 @@ struct UNet {
     __half* feat_staging = nullptr;    // for forward_ncdhw / forward_host
     float* out_staging = nullptr;
     std::string error;
-    // whole-forward CUDA graph, keyed by (batch, input pointer, output pointer)
-    cudaGraphExec_t gexec = nullptr;
-    const void* g_feat = nullptr;
-    float* g_out = nullptr;
-    int g_nb = 0;
+    // whole-forward CUDA graphs, keyed by (batch, input pointer, output pointer); a few entries so that callers that
+    // alternate between buffers (double-buffered host pipeline) replay instead of re-capturing
+    struct GraphEntry { cudaGraphExec_t exec = nullptr; const void* feat = nullptr; float* out = nullptr; int nb = 0; };
+    static constexpr int kGraphSlots = 4;
+    GraphEntry graphs[kGraphSlots];
+    int graph_next = 0;
     bool use_graph = true;
 
     ~UNet() {
-        if (gexec) cudaGraphExecDestroy(gexec);
+        for (auto& g : graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
         for (auto& c : convs) conv_plan_destroy(c->plan);
         for (void* p : allocs) cudaFree(p);
     }
@@ -487,8 +488,12 @@ static int enqueue_ops(UNet* u, cudaStream_t st) {
 static int run_ops(UNet* u, int batch, const void* feat, float* out, cudaStream_t st) {
     u->cur_nb = batch;
     if (u->use_graph) {
-        if (!(u->gexec && u->g_nb == batch && u->g_feat == feat && u->g_out == out)) {
-            if (u->gexec) { cudaGraphExecDestroy(u->gexec); u->gexec = nullptr; }
+        UNet::GraphEntry* hit = nullptr;
+        for (auto& g : u->graphs) if (g.exec && g.nb == batch && g.feat == feat && g.out == out) hit = &g;
+        if (!hit) {
+            UNet::GraphEntry& slot = u->graphs[u->graph_next];
+            u->graph_next = (u->graph_next + 1) % UNet::kGraphSlots;
+            if (slot.exec) { cudaGraphExecDestroy(slot.exec); slot.exec = nullptr; }
             cudaStream_t cs;                      // the caller's stream may be the legacy default stream, which cannot capture
             cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking);
             cudaGraph_t g = nullptr;
@@ -497,14 +502,14 @@ static int run_ops(UNet* u, int batch, const void* feat, float* out, cudaStream_
                 const int rc = enqueue_ops(u, cs);
                 ok = (cudaStreamEndCapture(cs, &g) == cudaSuccess) && g && rc == 0;
             }
-            if (ok) ok = cudaGraphInstantiate(&u->gexec, g, 0) == cudaSuccess;
+            if (ok) ok = cudaGraphInstantiate(&slot.exec, g, 0) == cudaSuccess;
             if (g) cudaGraphDestroy(g);
             cudaStreamDestroy(cs);
-            if (!ok) { cudaGetLastError(); u->gexec = nullptr; u->use_graph = false; }
-            u->g_nb = batch; u->g_feat = feat; u->g_out = out;
+            if (!ok) { cudaGetLastError(); slot.exec = nullptr; u->use_graph = false; }
+            else { slot.nb = batch; slot.feat = feat; slot.out = out; hit = &slot; }
         }
-        if (u->gexec) {
-            if (cudaGraphLaunch(u->gexec, st) != cudaSuccess) { u->error = "cudaGraphLaunch failed"; return 1; }
+        if (hit && hit->exec) {
+            if (cudaGraphLaunch(hit->exec, st) != cudaSuccess) { u->error = "cudaGraphLaunch failed"; return 1; }
             return 0;
         }
     }

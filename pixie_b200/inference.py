@@ -29,6 +29,7 @@ class MaterialFieldPredictor:
         self.device = torch.device(device)
         self.grid_size, self.feature_channels = grid_size, feature_channels
         self.n_classes, self.max_batch = num_material_classes, max_batch
+        self._pipe = None
         self._feat_dev: Optional[torch.Tensor] = None
         self._packed_dev: Optional[torch.Tensor] = None
 
@@ -37,10 +38,10 @@ class MaterialFieldPredictor:
         self.cont_network.load_state_dict(cont_sd, strict=strict)
         return self
 
-    def predict(self, feat_ndhwc_f16: torch.Tensor):
+    def predict(self, feat_ndhwc_f16: torch.Tensor, seg_out: Optional[torch.Tensor] = None, cont_out: Optional[torch.Tensor] = None):
         """Device fp16 (N, D, H, W, C) -> (seg_logits (N, n_classes, D,H,W), cont_pred (N, 3, D,H,W)) fp32."""
-        return (self.seg_network.forward_channels_last_f16(feat_ndhwc_f16),
-                self.cont_network.forward_channels_last_f16(feat_ndhwc_f16))
+        return (self.seg_network.forward_channels_last_f16(feat_ndhwc_f16, seg_out),
+                self.cont_network.forward_channels_last_f16(feat_ndhwc_f16, cont_out))
 
     def pack(self, seg_logits: torch.Tensor, cont_pred: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """(N, 3 + n_classes, D, H, W): continuous channels + one-hot argmax, as sample_*_pred.npy."""
@@ -51,6 +52,47 @@ class MaterialFieldPredictor:
         _lib.check(_lib.load().pixie_pack_predictions(C.c_void_p(seg_logits.data_ptr()), C.c_void_p(cont_pred.data_ptr()),
                                                       C.c_void_p(out.data_ptr()), n, G ** 3, self.n_classes, C.c_void_p(st)))
         return out
+
+    def predict_packed_host_stream(self, feats_pinned, outs_pinned=None):
+        """Many scenes end to end with HOST buffers, software-pipelined: while scene i runs through the two networks, scene i+1's
+        grid (268 MB at 64^3 x 512) is already crossing PCIe on a copy stream into the other of two device buffers. Per scene the
+        same work as `predict_packed_host` (H2D grid, both networks, packing, D2H field); returns the list of pinned outputs after
+        everything has finished. `feats_pinned`: sequence of pinned fp16 (N, D, H, W, C) tensors (N <= max_batch)."""
+        feats = list(feats_pinned)
+        G = self.grid_size
+        if outs_pinned is None:
+            outs_pinned = [torch.empty((f.shape[0], 3 + self.n_classes, G, G, G), dtype=torch.float32).pin_memory() for f in feats]
+        with torch.cuda.device(self.device):
+            if self._pipe is None:
+                nb = self.max_batch
+                self._pipe = {
+                    "in": [torch.empty((nb, G, G, G, self.feature_channels), dtype=torch.float16, device=self.device) for _ in range(2)],
+                    "out": [torch.empty((nb, 3 + self.n_classes, G, G, G), dtype=torch.float32, device=self.device) for _ in range(2)],
+                    # fixed network outputs per slot: the forward is a CUDA graph keyed by its input / output addresses
+                    "seg": [torch.empty((nb, self.n_classes, G, G, G), dtype=torch.float32, device=self.device) for _ in range(2)],
+                    "cont": [torch.empty((nb, 3, G, G, G), dtype=torch.float32, device=self.device) for _ in range(2)],
+                    "copy_stream": torch.cuda.Stream(device=self.device),
+                }
+            P = self._pipe
+            main = torch.cuda.current_stream(self.device)
+            cs = P["copy_stream"]
+            copied = [torch.cuda.Event() for _ in feats]
+            consumed = [torch.cuda.Event() for _ in feats]
+            cs.wait_stream(main)
+            for i, f in enumerate(feats):
+                n, slot = f.shape[0], i % 2
+                with torch.cuda.stream(cs):
+                    if i >= 2:
+                        cs.wait_event(consumed[i - 2])          # the networks are done reading this input slot
+                    P["in"][slot][:n].copy_(f, non_blocking=True)
+                    copied[i].record(cs)
+                main.wait_event(copied[i])
+                seg, cont = self.predict(P["in"][slot][:n], P["seg"][slot][:n], P["cont"][slot][:n])
+                consumed[i].record(main)
+                self.pack(seg, cont, P["out"][slot][:n])
+                outs_pinned[i].copy_(P["out"][slot][:n], non_blocking=True)     # stream-ordered: slot reuse two scenes later is safe
+            main.synchronize()
+        return outs_pinned
 
     def predict_packed_host(self, feat_pinned: torch.Tensor, out_pinned: Optional[torch.Tensor] = None) -> torch.Tensor:
         """End to end with HOST buffers: pinned fp16 (N, D, H, W, C) -> pinned fp32 (N, 3+n_classes, D,H,W).

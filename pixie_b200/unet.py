@@ -218,7 +218,7 @@ class _B200UNet:
                                                         C.c_void_p(out[b0:b0 + nb].data_ptr()), C.c_void_p(st)))
         return out
 
-    def forward_channels_last_f16(self, feat_ndhwc: torch.Tensor) -> torch.Tensor:
+    def forward_channels_last_f16(self, feat_ndhwc: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Fast path: float16 (N, D, H, W, C) on the device — the on-disk layout of
         clip_features_features.npy (voxelize.py:86,111), no conversion pass."""
         self._ensure_built()
@@ -230,7 +230,10 @@ class _B200UNet:
             raise ValueError("channels-last fast path needs feature_channels % 64 == 0")
         x = feat_ndhwc.to(self._device).contiguous()
         n = x.shape[0]
-        out = torch.empty((n, self.out_channels, G, G, G), dtype=torch.float32, device=self._device)
+        if out is None:
+            out = torch.empty((n, self.out_channels, G, G, G), dtype=torch.float32, device=self._device)
+        elif tuple(out.shape) != (n, self.out_channels, G, G, G) or out.dtype != torch.float32 or not out.is_contiguous():
+            raise ValueError("out must be a contiguous float32 (N, out_channels, D, H, W) device tensor")
         with torch.cuda.device(self._device):
             st = torch.cuda.current_stream().cuda_stream
             for b0 in range(0, n, self.max_batch):

@@ -100,6 +100,24 @@ def test_input_layout_paths_agree(built_lib, cuda_dev):
         net.forward_host(torch.zeros(3, G, G, G, C, dtype=torch.float16))
 
 
+def test_pipelined_host_stream_equals_single_calls(built_lib, cuda_dev):
+    """predict_packed_host_stream (double-buffered H2D overlapping the networks) = predict_packed_host scene by scene,
+    including when the two input slots and the graph cache are cycled more than once."""
+    from pixie_b200.inference import MaterialFieldPredictor
+    C, G = 64, 16
+    seg, reg = O.build_pair(C, G, seed=6)
+    pred = MaterialFieldPredictor(feature_channels=C, grid_size=G, device="cuda:0", max_batch=1, precision="fp16x3", **O.DEFAULT_CFG)
+    pred.load_state_dicts(seg.state_dict(), reg.state_dict())
+    scenes = [O.synthetic_features(1, C, G, seed=10 + i).permute(0, 2, 3, 4, 1).contiguous().to(torch.float16).pin_memory() for i in range(5)]
+    single = [pred.predict_packed_host(s).clone() for s in scenes]
+    piped = pred.predict_packed_host_stream(scenes)
+    piped2 = pred.predict_packed_host_stream(scenes[::-1])
+    for i in range(5):
+        assert (piped[i][:, :3] - single[i][:, :3]).abs().max() < 1e-4
+        assert (piped[i][:, 3:] == single[i][:, 3:]).float().mean() > 0.9999          # one-hot argmax
+        assert (piped2[4 - i][:, :3] - single[i][:, :3]).abs().max() < 1e-4
+
+
 @pytest.mark.parametrize("C", [3, 32])
 def test_projector_variants(built_lib, cuda_dev, C):
     """rgb / occupancy feature types: single-layer projector; feature_channels == cond_dim: none."""
