@@ -357,6 +357,9 @@ conv3d_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
             __syncwarp();
         };
         const bool wide_ok = !p.out_planar && ((p.out_ld & 3) == 0) && ((p.out_c0 & 3) == 0);
+        // 256-bit accesses need 32-byte aligned rows (cudaMalloc'ed bases are 256-byte aligned)
+        const bool wide8_ok = wide_ok && ((p.out_ld & 7) == 0) && ((p.out_c0 & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 31) == 0) &&
+                              (p.residual == nullptr || (reinterpret_cast<uintptr_t>(p.residual) & 31) == 0) && !(p.debug_flags & 8);
         for (int wi = blockIdx.x; wi < total_items && ok; wi += gridDim.x) {
             const TileCoord t = decode_tile(p, wi);
             ok = mbar_wait(&ctl->tfull[as], aph, abort_flag);
@@ -407,6 +410,9 @@ conv3d_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
 #pragma unroll
                                 for (int j = 0; j < 8; ++j)
                                     red_add_v4(p.out + base + 4 * j, f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                            } else if (wide8_ok) {
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) st_global_v8(p.out + base + 8 * j, f + 8 * j);    // one full sector per store
                             } else {
                                 float4* op = reinterpret_cast<float4*>(p.out + base);
 #pragma unroll
@@ -428,13 +434,23 @@ conv3d_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
                         const long long base0 = ((long long)t.nb * DHW + ((long long)(t.d0 + d) * p.H + hh) * p.W + ww) * p.out_ld + p.out_c0 + ch0;
                         float4 r0[8], r1[8];
                         if (use_res) {
-                            const float4* rp = reinterpret_cast<const float4*>(p.residual + base0);
+                            if (wide8_ok) {
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) r0[j] = __ldg(rp + j);
-                            if (two) {
-                                const float4* rq = reinterpret_cast<const float4*>(p.residual + base0 + plane_ld);
+                                for (int j = 0; j < 4; ++j) ld_global_nc_v8(p.residual + base0 + 8 * j, reinterpret_cast<float*>(&r0[2 * j]));
+                                if (two) {
 #pragma unroll
-                                for (int j = 0; j < 8; ++j) r1[j] = __ldg(rq + j);
+                                    for (int j = 0; j < 4; ++j)
+                                        ld_global_nc_v8(p.residual + base0 + plane_ld + 8 * j, reinterpret_cast<float*>(&r1[2 * j]));
+                                }
+                            } else {
+                                const float4* rp = reinterpret_cast<const float4*>(p.residual + base0);
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) r0[j] = __ldg(rp + j);
+                                if (two) {
+                                    const float4* rq = reinterpret_cast<const float4*>(p.residual + base0 + plane_ld);
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) r1[j] = __ldg(rq + j);
+                                }
                             }
                         }
                         tmem_ld_wait();
@@ -830,6 +846,7 @@ int conv_plan_create(const ConvDesc& d, int* d_err_flag, ConvPlan& plan, char* e
     p.stats_scalar = d.stats_scalar ? 1 : 0;
     p.desc_xor = 0;
     p.debug_flags = 0;
+    if (const char* e = getenv("PIXIE_CONV_DEBUG")) p.debug_flags = atoi(e);    // bring-up A/B switches (see conv3d_igemm.cuh)
     plan.out_bytes = d.out_planar ? (size_t)d.NB * d.Cout * d.D * d.H * d.W * 4
                                   : (size_t)d.NB * d.D * d.H * d.W * p.out_ld * 4;
 

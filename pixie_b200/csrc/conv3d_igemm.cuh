@@ -80,7 +80,8 @@ struct ConvKernelParams {
     int* err_flag;           // device int, set non-zero on pipeline timeout
     uint64_t desc_xor;       // bring-up only: xor into every smem matrix descriptor (0 in product use)
     int debug_flags;         // bring-up only, timing experiments (results are WRONG when set): 1 = epilogue skips its body,
-                             // 2 = producer stops issuing TMA once every stage was filled
+                             // 2 = producer stops issuing TMA once every stage was filled; 8 = epilogue uses 128-bit instead of
+                             // 256-bit global accesses (results stay correct)
 };
 
 // One activation source of a convolution.
