@@ -97,6 +97,18 @@ int pixie_knn_assign(const float* query_dev, int n_query, const float* pos_dev, 
                      float nn_distance_threshold, int weighted, const float defaults_host[4], int default_material, int default_part,
                      float* out_density_dev, float* out_E_dev, float* out_nu_dev, int* out_material_dev, int* out_part_dev,
                      float* out_conf_dev, int* n_too_far_host, void* stream);
+/* ---- either side of the substep loop.
+ * pixie_particle_volume: get_particle_volume, PG/particle_filling/filling.py:247-288 (Taichi in the reference): particles per cell
+ * of a grid_n^3 grid of spacing grid_dx, vol = grid_dx^3 / count. Positions outside the grid are clamped to the border cells
+ * (the reference indexes out of range). Synchronises `stream`. */
+int pixie_particle_volume(const float* pos_dev, int n, int grid_n, float grid_dx, float* vol_dev, void* stream);
+/* pixie_frame_transform: per-frame hand-over to the rasteriser, gs_simulation.py:591-600 with utils/transformation_utils.py:19-20,
+ * 57-87, 101-126: pos_render = apply_inverse_rotations(mean + (pos - (1,1,1+z_shift)) / scale, Rs); cov_render =
+ * apply_inverse_cov_rotations(cov / scale^2, Rs) on the 6 upper-triangular entries (cov_dev may be NULL). rotations_host:
+ * [n_rot][9] row-major in the order they were applied forward (n_rot <= 8). */
+int pixie_frame_transform(const float* pos_dev, const float* cov_dev, int n, float z_shift_value, float scale_origin,
+                          const float original_mean_pos_host[3], const float* rotations_host, int n_rot, float* pos_out_dev,
+                          float* cov_out_dev, void* stream);
 /* Number of kernel launches one forward() issues (for gpu_launches accounting) and algorithmic
  * FLOPs of one forward at batch 1 (2 * MACs of every Conv3d/Conv1d of the reference graph). */
 int pixie_unet_launch_count(pixie_unet_t h);

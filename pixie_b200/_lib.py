@@ -88,6 +88,9 @@ _SIGNATURES = {
     "pixie_knn_assign": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                    C.c_int, C.c_float, C.c_int, C.POINTER(C.c_float), C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.c_void_p]),
+    "pixie_particle_volume": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p]),
+    "pixie_frame_transform": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int,
+                                        C.c_void_p, C.c_void_p, C.c_void_p]),
     "pixie_mpm_bind_grid": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pixie_mpm_set_slab": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "pixie_mpm_set_active_count": (C.c_int, [C.c_void_p, C.c_int]),

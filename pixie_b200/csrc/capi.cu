@@ -97,6 +97,21 @@ int pixie_knn_assign(const float* query, int nq, const float* pos, const float* 
         return set_err("knn_assign failed");
     return 0;
 }
+int pixie_particle_volume(const float* pos, int n, int grid_n, float grid_dx, float* vol, void* stream) {
+    if (!pos || !vol) return set_err("null argument");
+    if (grid_n < 1 || !(grid_dx > 0.f)) return set_err("particle_volume: bad grid");
+    if (require_device()) return 1;
+    if (pixie::particle_volume(pos, n, grid_n, grid_dx, vol, (cudaStream_t)stream)) return set_err("particle_volume failed");
+    return 0;
+}
+int pixie_frame_transform(const float* pos, const float* cov, int n, float z_shift, float scale, const float mean[3], const float* rotations,
+                          int n_rot, float* pos_out, float* cov_out, void* stream) {
+    if (!pos || !mean || !pos_out || (cov && !cov_out) || (n_rot > 0 && !rotations)) return set_err("null argument");
+    if (n_rot < 0 || n_rot > 8) return set_err("frame_transform: at most 8 rotations");
+    if (require_device()) return 1;
+    if (pixie::frame_transform(pos, cov, n, z_shift, scale, mean, rotations, n_rot, pos_out, cov_out, (cudaStream_t)stream)) return set_err("frame_transform failed");
+    return 0;
+}
 int pixie_pack_predictions(const float* seg_logits_dev, const float* cont_dev, float* out_dev, int batch, int64_t voxels, int n_classes, void* stream) {
     if (!seg_logits_dev || !cont_dev || !out_dev) return set_err("null argument");
     if (require_device()) return 1;

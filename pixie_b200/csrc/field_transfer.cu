@@ -183,6 +183,72 @@ knn_assign_kernel(const KnnArgs a) {
     }
 }
 
+
+// ---- per-frame export
+// get_particle_volume (PG/particle_filling/filling.py:247-288): particles per cell of a grid_n^3 grid, vol = dx^3 / count.
+__device__ __forceinline__ int cell_of(float p, float dx, int n) {
+    const int i = (int)floorf(p / dx);            // ti.floor(p / grid_dx, dtype=int) in f32
+    return min(max(i, 0), n - 1);                 // the Taichi kernel indexes out of range here; we clamp
+}
+__global__ void volume_count_kernel(const float* __restrict__ pos, int n, float dx, int gn, int* __restrict__ grid) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const int i = cell_of(pos[3 * p], dx, gn), j = cell_of(pos[3 * p + 1], dx, gn), k = cell_of(pos[3 * p + 2], dx, gn);
+    atomicAdd(grid + ((size_t)i * gn + j) * gn + k, 1);
+}
+__global__ void volume_assign_kernel(const float* __restrict__ pos, int n, float dx, int gn, const int* __restrict__ grid, float* __restrict__ vol) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const int i = cell_of(pos[3 * p], dx, gn), j = cell_of(pos[3 * p + 1], dx, gn), k = cell_of(pos[3 * p + 2], dx, gn);
+    vol[p] = (dx * dx * dx) / (float)grid[((size_t)i * gn + j) * gn + k];
+}
+
+// gs_simulation.py:591-600: pos_render = apply_inverse_rotations(undotransform2origin(undoshift2center111(pos, z_shift), scale, mean), Rs),
+// cov3D_render = apply_inverse_cov_rotations(cov / scale^2, Rs)   (utils/transformation_utils.py:19-20, 57-87, 101-126)
+struct FrameArgs {
+    const float *pos, *cov; int n;
+    float z_shift, scale, mean[3];
+    float R[8][9]; int n_rot;
+    float *pos_out, *cov_out;
+};
+__global__ void frame_transform_kernel(const FrameArgs a) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= a.n) return;
+    float v[3] = {a.pos[3 * p] - 1.0f - 0.0f, a.pos[3 * p + 1] - 1.0f - 0.0f, a.pos[3 * p + 2] - 1.0f - a.z_shift};
+#pragma unroll
+    for (int d = 0; d < 3; ++d) v[d] = a.mean[d] + v[d] / a.scale;
+    for (int r = a.n_rot - 1; r >= 0; --r) {               // torch.mm(position, R): row vector times R
+        const float* R = a.R[r];
+        const float x = v[0] * R[0] + v[1] * R[3] + v[2] * R[6];
+        const float y = v[0] * R[1] + v[1] * R[4] + v[2] * R[7];
+        const float z = v[0] * R[2] + v[1] * R[5] + v[2] * R[8];
+        v[0] = x; v[1] = y; v[2] = z;
+    }
+    a.pos_out[3 * p] = v[0]; a.pos_out[3 * p + 1] = v[1]; a.pos_out[3 * p + 2] = v[2];
+    if (!a.cov) return;
+    const float s2 = a.scale * a.scale;
+    float u[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) u[i] = a.cov[6 * p + i] / s2;
+    float M[9] = {u[0], u[1], u[2], u[1], u[3], u[4], u[2], u[4], u[5]};      // get_mat_from_upper
+    for (int r = a.n_rot - 1; r >= 0; --r) {               // apply_cov_rotation(cov, R.T): R^T (cov R)
+        const float* R = a.R[r];
+        float T[9], O[9];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) T[3 * i + j] = M[3 * i] * R[j] + M[3 * i + 1] * R[3 + j] + M[3 * i + 2] * R[6 + j];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) O[3 * i + j] = R[i] * T[j] + R[3 + i] * T[3 + j] + R[6 + i] * T[6 + j];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) M[i] = O[i];
+    }
+    float* o = a.cov_out + 6 * (size_t)p;                   // get_uppder_from_mat
+    o[0] = M[0]; o[1] = M[1]; o[2] = M[2]; o[3] = M[4]; o[4] = M[5]; o[5] = M[8];
+}
+
 }  // namespace
 
 int field_extract(const float* pred, int n_classes, const float* mask, int D, const double ranges[6], const double bmin[3], const double bmax[3],
@@ -228,6 +294,33 @@ int knn_assign(const float* query, int nq, const float* pos, const float* densit
     rc |= cudaStreamSynchronize(st) != cudaSuccess;
     cudaFree(d_cnt);
     return rc || cudaGetLastError() != cudaSuccess;
+}
+
+int particle_volume(const float* pos, int n, int grid_n, float grid_dx, float* vol, cudaStream_t st) {
+    int* grid = nullptr;
+    const size_t cells = (size_t)grid_n * grid_n * grid_n;
+    if (cudaMalloc(&grid, cells * sizeof(int)) != cudaSuccess) return 1;
+    cudaMemsetAsync(grid, 0, cells * sizeof(int), st);
+    if (n > 0) {
+        volume_count_kernel<<<(n + 255) / 256, 256, 0, st>>>(pos, n, grid_dx, grid_n, grid);
+        volume_assign_kernel<<<(n + 255) / 256, 256, 0, st>>>(pos, n, grid_dx, grid_n, grid, vol);
+    }
+    const int rc = cudaStreamSynchronize(st) != cudaSuccess;
+    cudaFree(grid);
+    return rc || cudaGetLastError() != cudaSuccess;
+}
+
+int frame_transform(const float* pos, const float* cov, int n, float z_shift, float scale, const float mean[3], const float* rotations, int n_rot,
+                    float* pos_out, float* cov_out, cudaStream_t st) {
+    if (n_rot < 0 || n_rot > 8) return 2;
+    FrameArgs a{};
+    a.pos = pos; a.cov = cov; a.n = n; a.z_shift = z_shift; a.scale = scale;
+    for (int d = 0; d < 3; ++d) a.mean[d] = mean[d];
+    for (int r = 0; r < n_rot; ++r)
+        for (int i = 0; i < 9; ++i) a.R[r][i] = rotations[9 * r + i];
+    a.n_rot = n_rot; a.pos_out = pos_out; a.cov_out = cov_out;
+    if (n > 0) frame_transform_kernel<<<(n + 255) / 256, 256, 0, st>>>(a);
+    return cudaGetLastError() != cudaSuccess;
 }
 
 }  // namespace pixie

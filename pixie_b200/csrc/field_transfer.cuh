@@ -17,4 +17,11 @@ int knn_assign(const float* query, int nq, const float* pos, const float* densit
                int def_part, float* o_density, float* o_E, float* o_nu, int* o_material, int* o_part, float* o_conf, int* n_too_far_host,
                cudaStream_t st);
 
+// get_particle_volume (filling.py:247-288): vol[p] = dx^3 / (particles in p's cell of the grid_n^3 grid). Synchronises the stream.
+int particle_volume(const float* pos, int n, int grid_n, float grid_dx, float* vol, cudaStream_t st);
+// Per-frame export to the renderer's frame (gs_simulation.py:591-600): positions and (optionally) upper-triangular covariances.
+// rotations: host array [n_rot][9] row-major, applied in reverse order like apply_inverse_rotations.
+int frame_transform(const float* pos, const float* cov, int n, float z_shift, float scale, const float mean[3], const float* rotations, int n_rot,
+                    float* pos_out, float* cov_out, cudaStream_t st);
+
 }  // namespace pixie
