@@ -67,24 +67,32 @@ struct TileCoord {
     int nb, d0, h0, w0, n0, ph_begin, ph_end, split, tde;
 };
 
+// Tile coordinates of work item `wi`. On the MMA issuer's critical path once per tile (r01 trace: ~1000 cycles with signed and
+// 64-bit divisions), so: unsigned 32-bit divisions only, and none at all for the split-K bookkeeping of unsplit convolutions.
 __device__ __forceinline__ TileCoord decode_tile(const ConvKernelParams& p, int wi) {
     TileCoord t;
-    t.split = wi % p.split_k;
-    int rest = wi / p.split_k;
-    int nt = rest % p.n_tiles;
-    int m = rest / p.n_tiles;
-    int tw = m % p.tiles_w;
-    m /= p.tiles_w;
-    int th = m % p.tiles_h;
-    m /= p.tiles_h;
-    int td = m % p.tiles_d;
-    t.nb = m / p.tiles_d;
-    t.d0 = td * p.TD;
-    t.h0 = th * p.TH;
-    t.w0 = tw * p.TW;
-    t.n0 = nt * p.block_n;
-    t.ph_begin = (int)(((long long)t.split * p.n_phases) / p.split_k);
-    t.ph_end = (int)(((long long)(t.split + 1) * p.n_phases) / p.split_k);
+    unsigned rest = (unsigned)wi;
+    if (p.split_k == 1) {
+        t.split = 0; t.ph_begin = 0; t.ph_end = p.n_phases;
+    } else {
+        const unsigned sk = (unsigned)p.split_k;
+        t.split = (int)(rest % sk);
+        rest /= sk;
+        t.ph_begin = (int)(((unsigned)t.split * (unsigned)p.n_phases) / sk);            // n_phases * split_k < 2^31 (checked at plan time)
+        t.ph_end = (int)((((unsigned)t.split + 1u) * (unsigned)p.n_phases) / sk);
+    }
+    const unsigned nt = rest % (unsigned)p.n_tiles;
+    unsigned m = rest / (unsigned)p.n_tiles;
+    const unsigned tw = m % (unsigned)p.tiles_w;
+    m /= (unsigned)p.tiles_w;
+    const unsigned th = m % (unsigned)p.tiles_h;
+    m /= (unsigned)p.tiles_h;
+    const unsigned td = m % (unsigned)p.tiles_d;
+    t.nb = (int)(m / (unsigned)p.tiles_d);
+    t.d0 = (int)td * p.TD;
+    t.h0 = (int)th * p.TH;
+    t.w0 = (int)tw * p.TW;
+    t.n0 = (int)nt * p.block_n;
     t.tde = min(p.TD, p.D - t.d0);
     return t;
 }
@@ -791,6 +799,7 @@ int conv_plan_create(const ConvDesc& d, int* d_err_flag, ConvPlan& plan, char* e
         while (items * split < 120 && split * 2 <= p.n_phases && split < 64) split *= 2;
     }
     split = std::max(1, std::min(split, p.n_phases));
+    if ((long long)p.n_phases * (split + 1) >= (1ll << 31)) return fail("too many phases for the split-K bookkeeping");
     p.split_k = split;
     p.atomic_out = split > 1;
     plan.needs_zero = split > 1;
