@@ -218,10 +218,10 @@ int pixie_mpm_apply_additional_params(pixie_mpm_t h, const float* boxes, int n_b
 int pixie_mpm_select_box(pixie_mpm_t h, const float point[3], const float size[3], int* mask_dev, void* stream);
 int pixie_mpm_select_cylinder(pixie_mpm_t h, const float point[3], const float normal[3],
                               float half_height, float radius, int* mask_dev, void* stream);
-/* The solver keeps a cell-sorted private copy of the particle state between steps. pixie_mpm_sync writes
- * results back into the bound arrays (no-op if they are current) and must precede any read of them; every
- * other entry point that touches the bound arrays calls it internally. After a sync the caller may modify
- * its arrays: the next step re-reads them. */
+/* The default path works in place on the bound arrays (pixie_mpm_sync is then a no-op). The opt-in tiled path
+ * (PIXIE_MPM_TILED=1) keeps a tile-sorted private copy of the particle state between steps: pixie_mpm_sync writes the
+ * results back into the bound arrays and must precede any read of them; every other entry point that touches the bound
+ * arrays calls it internally. After a sync the caller may modify its arrays: the next step re-reads them. */
 int pixie_mpm_sync(pixie_mpm_t h, void* stream);
 /* ---- Spatially sharded rollout (BASELINE config 5: one large scene, slab decomposition along x; no reference
  * counterpart — the reference hard-wires "cuda:0", gs_simulation.py:441). One handle per rank holds the particles whose
