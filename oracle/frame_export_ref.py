@@ -24,18 +24,16 @@ def get_particle_volume(pos: np.ndarray, grid_n: int, grid_dx: float, unifrom: b
     return vol
 
 
+_FULL_FROM_UPPER = [0, 1, 2, 1, 3, 4, 2, 4, 5]      # symmetric 3x3 (row-major) from (xx, xy, xz, yy, yz, zz)   transformation_utils.py:63-77
+_UPPER_FROM_FULL = [0, 1, 2, 4, 5, 8]               # and back                                                   :80-87
+
+
 def _mat_from_upper(u):
-    u = u.reshape(-1, 6)
-    m = np.zeros((len(u), 9), u.dtype)
-    m[:, :3] = u[:, :3]; m[:, 3] = u[:, 1]; m[:, 4] = u[:, 3]; m[:, 5] = u[:, 4]; m[:, 6] = u[:, 2]; m[:, 7] = u[:, 4]; m[:, 8] = u[:, 5]
-    return m.reshape(-1, 3, 3)
+    return u.reshape(-1, 6)[:, _FULL_FROM_UPPER].reshape(-1, 3, 3)
 
 
 def _upper_from_mat(m):
-    m = m.reshape(-1, 9)
-    u = np.zeros((len(m), 6), m.dtype)
-    u[:, :3] = m[:, :3]; u[:, 3] = m[:, 4]; u[:, 4] = m[:, 5]; u[:, 5] = m[:, 8]
-    return u
+    return m.reshape(-1, 9)[:, _UPPER_FROM_FULL]
 
 
 def render_frame_transform(pos, cov, z_shift_value, scale_origin, original_mean_pos, rotation_matrices):

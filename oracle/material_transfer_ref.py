@@ -13,97 +13,104 @@ cases in tests/test_material_transfer.py only. Only tests/ may import this file.
 """
 from __future__ import annotations
 
-from collections import Counter
-
 import numpy as np
 
 DEFAULT_VALUES = {"density": 1000.0, "E": 1e6, "nu": 0.3, "part_label": 0, "material_id": "stationary"}   # material_field.py:16-23
 STATIONARY_ID = 6                                                                                       # mpm_solver_warp.py:10-26
 
 
+def _from_unit(c: np.ndarray, lo: float, hi: float) -> np.ndarray:
+    """[-1, 1] -> [lo, hi]; float32 array arithmetic with Python-float bounds, evaluated in the reference's order
+    ((c + 1) * (hi - lo) / 2 + lo, map_pred_to_coords.py:62-71)."""
+    return (c + 1.0) * (hi - lo) / 2.0 + lo
+
+
 def unscale_prediction(pred_tensor: np.ndarray, r: dict) -> np.ndarray:
-    cont = pred_tensor[:3]
-    cont = np.clip(cont, -1.0, 1.0)
+    """map_pred_to_coords.py:41-75: channels 0/1 are log10(density), log10(E), channel 2 is nu; the class channels pass through."""
     out = pred_tensor.copy().astype(np.float32)
-    dens_log = (cont[0] + 1.0) * (r["density_max"] - r["density_min"]) / 2.0 + r["density_min"]
-    out[0] = 10 ** dens_log
-    E_log = (cont[1] + 1.0) * (r["E_max"] - r["E_min"]) / 2.0 + r["E_min"]
-    out[1] = 10 ** E_log
-    out[2] = (cont[2] + 1.0) * (r["nu_max"] - r["nu_min"]) / 2.0 + r["nu_min"]
+    unit = np.clip(pred_tensor[:3], -1.0, 1.0)                 # the network output is not strictly bounded
+    out[0] = 10 ** _from_unit(unit[0], r["density_min"], r["density_max"])
+    out[1] = 10 ** _from_unit(unit[1], r["E_min"], r["E_max"])
+    out[2] = _from_unit(unit[2], r["nu_min"], r["nu_max"])
     return out
 
 
 def vertex_table(scaled_pred: np.ndarray, mask: np.ndarray, min_bounds, max_bounds, r: dict) -> dict:
-    pred = unscale_prediction(scaled_pred, r)
-    grid_shape = mask.shape
-    cont, seg = pred[:3, :], pred[3:, :]
-    material_id = seg[0] if seg.shape[0] == 1 else np.argmax(seg, axis=0)          # get_mat_id :122-126
-    x = np.linspace(min_bounds[0], max_bounds[0], grid_shape[0])
-    y = np.linspace(min_bounds[1], max_bounds[1], grid_shape[1])
-    z = np.linspace(min_bounds[2], max_bounds[2], grid_shape[2])
-    gx, gy, gz = np.meshgrid(x, y, z, indexing="ij")
-    coords = np.stack([gx, gy, gz], axis=-1)
-    valid = mask > 0
-    conf = np.max(seg, axis=0)[valid] if seg.shape[0] > 1 else np.ones(int(valid.sum()), dtype=np.float32)
-    return {"pos": coords[valid].astype(np.float32),                               # PLY fields are 'f4' / 'i4' (:222-231)
-            "density": cont[0][valid].astype(np.float32), "E": cont[1][valid].astype(np.float32), "nu": cont[2][valid].astype(np.float32),
-            "material_id": material_id[valid].astype(np.int32), "part_labels": material_id[valid].astype(np.int32),
-            "conf": conf.astype(np.float32)}
+    """The vertex records map_pred_to_ply writes (:198-245), as arrays: occupied voxels in C order, voxel centres from
+    np.linspace over the bounds (meshgrid 'ij'), id = argmax of the class channels, conf = their maximum."""
+    field = unscale_prediction(scaled_pred, r)
+    classes = field[3:]
+    ids = classes[0] if classes.shape[0] == 1 else np.argmax(classes, axis=0)            # get_mat_id :122-126
+    axes = [np.linspace(min_bounds[d], max_bounds[d], mask.shape[d]) for d in range(3)]
+    centres = np.stack(np.meshgrid(*axes, indexing="ij"), axis=-1)
+    keep = mask > 0
+    conf = np.max(classes, axis=0)[keep] if classes.shape[0] > 1 else np.ones(int(keep.sum()), dtype=np.float32)
+    f32 = lambda a: a[keep].astype(np.float32)                                          # PLY fields are 'f4' / 'i4' (:222-231)
+    return {"pos": centres[keep].astype(np.float32), "density": f32(field[0]), "E": f32(field[1]), "nu": f32(field[2]),
+            "material_id": ids[keep].astype(np.int32), "part_labels": ids[keep].astype(np.int32), "conf": conf.astype(np.float32)}
 
 
-class MaterialProperties:
-    def __init__(self, part_labels, densities, E_values, nu_values, material_ids, conf_values):
-        self.properties = {"part_labels": part_labels, "density": densities, "E": E_values, "nu": nu_values,
-                           "material_id": material_ids, "conf": conf_values}
+_CATEGORICAL = ("material_id", "part_labels")
+_ORDER = ("part_labels", "density", "E", "nu", "material_id", "conf")                     # MaterialProperties.properties order (:29-36)
 
-    def get_defaults(self, n_particles):
-        defaults = {}
-        for key, values in self.properties.items():
-            if key == "material_id":
-                default_val = STATIONARY_ID
-            elif key in ["part_labels"]:
-                default_val = DEFAULT_VALUES["part_label"]
+
+def _fallback_values(props: dict, n: int) -> dict:
+    """get_defaults (:38-50): 'stationary' for the material, 0 for the part label, the mean of everything else."""
+    out = {}
+    for name in _ORDER:
+        v = props[name]
+        if name == "material_id":
+            fill = STATIONARY_ID
+        elif name == "part_labels":
+            fill = DEFAULT_VALUES["part_label"]
+        else:
+            fill = np.mean(v) if len(v) > 0 else DEFAULT_VALUES.get(name, 0.0)
+        out[name] = np.full(n, fill, dtype=v.dtype if hasattr(v, "dtype") else np.float32)
+    return out
+
+
+def _first_most_frequent(values) -> int:
+    """Counter(values).most_common(1)[0][0]: highest count, ties resolved by first appearance."""
+    seen = list(dict.fromkeys(values.tolist()))
+    counts = [int(np.sum(values == s)) for s in seen]
+    return seen[int(np.argmax(counts))]                        # argmax returns the first maximum
+
+
+def _from_neighbours(props: dict, idx: np.ndarray, dist: np.ndarray, weighted: bool) -> dict:
+    """assign_from_neighbors (:52-86) for one particle: idx / dist = its k neighbours in ascending distance."""
+    w = 1.0 / (dist + 1e-8)
+    w = w / np.sum(w)
+    out = {}
+    for name in _ORDER:
+        v = props[name][idx]
+        if name in _CATEGORICAL:
+            if weighted:
+                labels, inverse = np.unique(v, return_inverse=True)
+                out[name] = labels[np.argmax(np.bincount(inverse, weights=w))]
             else:
-                default_val = np.mean(values) if len(values) > 0 else DEFAULT_VALUES.get(key, 0.0)
-            defaults[key] = np.full(n_particles, default_val, dtype=values.dtype if hasattr(values, "dtype") else np.float32)
-        return defaults
-
-    def assign_from_neighbors(self, particle_idx, neighbor_indices, distances, weighted=False):
-        results = {}
-        weights = 1.0 / (distances + 1e-8)
-        weights = weights / np.sum(weights)
-        for prop_name, prop_values in self.properties.items():
-            neighbor_values = prop_values[neighbor_indices]
-            if prop_name in ["material_id", "part_labels"]:
-                if weighted:
-                    unique_vals, inv_indices = np.unique(neighbor_values, return_inverse=True)
-                    votes = np.bincount(inv_indices, weights=weights)
-                    results[prop_name] = unique_vals[np.argmax(votes)]
-                else:
-                    results[prop_name] = Counter(neighbor_values).most_common(1)[0][0]
-            else:
-                results[prop_name] = np.dot(weights, neighbor_values) if weighted else np.mean(neighbor_values)
-        return results
+                out[name] = _first_most_frequent(v)
+        else:
+            out[name] = np.dot(w, v) if weighted else np.mean(v)
+    return out
 
 
 def perform_knn_smoothing(query_positions: np.ndarray, params: dict, k_smoothing_neighbors=10, nn_distance_threshold=0.1,
                           weighted_assignment=False):
+    """material_field.py:228-293 with scikit-learn's NearestNeighbors, as the reference."""
     from sklearn.neighbors import NearestNeighbors
-    n_particles = len(query_positions)
-    props = MaterialProperties(params["part_labels"], params["density"], params["E"], params["nu"], params["material_id"], params["conf"])
-    if len(props.properties["part_labels"]) == n_particles:
-        return tuple(props.properties.values())
-    nn_model = NearestNeighbors(n_neighbors=k_smoothing_neighbors, algorithm="auto").fit(params["pos"])
-    distances_all_k, k_indices = nn_model.kneighbors(query_positions)
-    too_far_mask = distances_all_k[:, 0] > nn_distance_threshold
-    n_too_far = int(np.sum(too_far_mask))
-    assert n_too_far <= 0.1 * n_particles
-    mapped = props.get_defaults(n_particles)
-    for i in np.where(~too_far_mask)[0]:
-        a = props.assign_from_neighbors(i, k_indices[i], distances_all_k[i], weighted_assignment)
-        for prop_name, value in a.items():
-            mapped[prop_name][i] = value
-    return tuple(mapped.values())
+    n = len(query_positions)
+    props = {"part_labels": params["part_labels"], "density": params["density"], "E": params["E"], "nu": params["nu"],
+             "material_id": params["material_id"], "conf": params["conf"]}
+    if len(props["part_labels"]) == n:                          # :236-238
+        return tuple(props[name] for name in _ORDER)
+    dist, idx = NearestNeighbors(n_neighbors=k_smoothing_neighbors, algorithm="auto").fit(params["pos"]).kneighbors(query_positions)
+    far = dist[:, 0] > nn_distance_threshold
+    assert int(np.sum(far)) <= 0.1 * n                          # :271
+    result = _fallback_values(props, n)
+    for i in np.flatnonzero(~far):
+        for name, value in _from_neighbours(props, idx[i], dist[i], weighted_assignment).items():
+            result[name][i] = value
+    return tuple(result[name] for name in _ORDER)
 
 
 def apply_additional_params(x: np.ndarray, densities, E_values, nu_values, material_ids, size=0.001):
