@@ -4,18 +4,21 @@
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load
  * this library; pixie_b200/ never does.
  *
- * PARITY UNPINNED: the arithmetic of the reference lives in warp-lang==0.10.1 (pinned in
- * third_party/PhysGaussian/requirements.txt:4), which is neither vendored in /root/reference nor
- * installed here, and the reference ships no tests, golden vectors or expected outputs for this
- * path.  This file restates the published algorithm of the reference's own
- * kernels, statement by statement:
+ * PINNED BY THE REFERENCE'S OWN SOURCE: the arithmetic of the reference lives in warp-lang==0.10.1 (pinned in
+ * third_party/PhysGaussian/requirements.txt:4), which is neither vendored in /root/reference nor installed here,
+ * and the reference ships no tests or golden vectors for this path.  But its kernels are plain
+ * Python syntax, so tests/golden/make_mpm_golden.py imports them from /root/reference and EXECUTES them on a float32
+ * `warp` stand-in (tests/golden/_fake_warp.py); the resulting fixture tests/golden/mpm_golden.npz (8 scenarios: every
+ * material id, return map, stress model, BC closure, selection/setup/export kernel; 1- and 20-substep checkpoints)
+ * is what tests/test_mpm_golden.py holds this file to (relative 5e-6 after one substep, masks / ids exact).
+ * This file restates, statement by statement:
  *     third_party/PhysGaussian/mpm_solver_warp/mpm_utils.py        (kernels, :10-663)
  *     third_party/PhysGaussian/mpm_solver_warp/mpm_solver_warp.py  (p2g2p :514-637, BCs :749-1210)
  *     third_party/PhysGaussian/mpm_solver_warp/warp_utils.py       (structs :6-183)
- * and is pinned only by self-consistency tests (tests/test_oracle_mpm.py: momentum conservation,
- * F = I fixed point, free fall, SVD against numpy.linalg.svd, analytic return-mapping cases).
- * wp.svd3 (Warp native/svd.h) is replaced by a one-sided Jacobi SVD with the same output convention
- * (U, V proper rotations, |sigma| sorted descending, sign of det F on the last singular value).
+ * Self-consistency tests stay (tests/test_oracle_mpm.py).  Still outside any pin: wp.svd3's own rounding (Warp
+ * native/svd.h) — replaced here by a one-sided Jacobi SVD with the same output convention (U, V proper rotations,
+ * |sigma| sorted descending, sign of det F on the last singular value); every use in the reference is of the
+ * invariant form U f(Sigma) V^T.
  *
  * Compiled twice: -DREAL=float (the reference's precision) and -DREAL=double (drift reference).
  */
@@ -593,6 +596,53 @@ void mpmref_compute_cov_from_F(sim_t* s) {      /* compute_cov_from_F, mpm_utils
         a = m3_mul(&F, &c0); Ft = m3_t(&F); c = m3_mul(&a, &Ft);
         real* o = s->f[F_COV] + 6 * (size_t)p;
         o[0] = c.m[0]; o[1] = c.m[1]; o[2] = c.m[2]; o[3] = c.m[4]; o[4] = c.m[5]; o[5] = c.m[8];
+    }
+}
+void mpmref_compute_bulk(sim_t* s) {            /* compute_bulk, mpm_utils.py:290-293 */
+    for (int p = 0; p < s->n; ++p) s->f[F_BULK][p] = s->f[F_LAM][p] + (real)(2. / 3.) * s->f[F_MU][p];
+}
+void mpmref_compute_R_from_F(sim_t* s) {        /* compute_R_from_F, mpm_utils.py:556-579 */
+    for (int p = 0; p < s->n; ++p) {
+        m3 F, U, V, Vt, R, Rt; real sg[3];
+        memcpy(F.m, s->f[F_FTRIAL] + 9 * (size_t)p, sizeof(F.m));
+        svd3(&F, &U, sg, &V);
+        if (m3_det(&U) < 0) { U.m[2] = -U.m[2]; U.m[5] = -U.m[5]; U.m[8] = -U.m[8]; }
+        if (m3_det(&V) < 0) { V.m[2] = -V.m[2]; V.m[5] = -V.m[5]; V.m[8] = -V.m[8]; }
+        Vt = m3_t(&V); R = m3_mul(&U, &Vt); Rt = m3_t(&R);
+        memcpy(s->f[F_R] + 9 * (size_t)p, Rt.m, sizeof(Rt.m));
+    }
+}
+/* apply_additional_params, mpm_utils.py:591-610: box = point3 size3 E nu density material */
+void mpmref_apply_additional_params(sim_t* s, const double* box) {
+    const real pt[3] = {(real)box[0], (real)box[1], (real)box[2]}, sz[3] = {(real)box[3], (real)box[4], (real)box[5]};
+    for (int p = 0; p < s->n; ++p) {
+        const real* x = s->f[F_X] + 3 * (size_t)p;
+        if (x[0] > pt[0] - sz[0] && x[0] < pt[0] + sz[0] && x[1] > pt[1] - sz[1] && x[1] < pt[1] + sz[1] &&
+            x[2] > pt[2] - sz[2] && x[2] < pt[2] + sz[2]) {
+            s->f[F_E][p] = (real)box[6]; s->f[F_NU][p] = (real)box[7]; s->f[F_DENSITY][p] = (real)box[8];
+            s->material[p] = (int)box[9];
+        }
+    }
+}
+/* selection_add_impulse_on_particles / selection_enforce_particle_velocity_translation, mpm_utils.py:613-645 */
+void mpmref_select_box(sim_t* s, const double* point, const double* size, int* mask) {
+    for (int p = 0; p < s->n; ++p) {
+        const real* x = s->f[F_X] + 3 * (size_t)p;
+        int in = 1;
+        for (int a = 0; a < 3; ++a) in = in && (RABS(x[a] - (real)point[a]) < (real)size[a]);
+        mask[p] = in;
+    }
+}
+/* selection_enforce_particle_velocity_cylinder, mpm_utils.py:648-663 */
+void mpmref_select_cylinder(sim_t* s, const double* point, const double* normal, double half_height, double radius, int* mask) {
+    const real nn[3] = {(real)normal[0], (real)normal[1], (real)normal[2]};
+    for (int p = 0; p < s->n; ++p) {
+        const real* x = s->f[F_X] + 3 * (size_t)p;
+        const real off[3] = {x[0] - (real)point[0], x[1] - (real)point[1], x[2] - (real)point[2]};
+        const real on = off[0] * nn[0] + off[1] * nn[1] + off[2] * nn[2];
+        const real h[3] = {off[0] - on * nn[0], off[1] - on * nn[1], off[2] - on * nn[2]};
+        const real hd = RSQRT(h[0] * h[0] + h[1] * h[1] + h[2] * h[2]);
+        mask[p] = (RABS(on) < (real)half_height && hd < (real)radius) ? 1 : 0;
     }
 }
 void mpmref_svd3(const double* F9, double* U9, double* sig3, double* V9) {

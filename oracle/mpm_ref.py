@@ -1,5 +1,6 @@
 """ORACLE (test infrastructure, not product code): ctypes wrapper of oracle/mpm_ref.c, the CPU
-restatement of the reference's Warp MPM kernels (PARITY UNPINNED — see the header of mpm_ref.c).
+restatement of the reference's Warp MPM kernels, pinned to the reference's own source through
+tests/golden/mpm_golden.npz (see the header of mpm_ref.c and tests/test_mpm_golden.py).
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this.
 """
@@ -46,9 +47,13 @@ def _lib(precision: str) -> C.CDLL:
     lib.mpmref_get_time.restype = C.c_double
     lib.mpmref_get_time.argtypes = [C.c_void_p]
     lib.mpmref_add_bc.argtypes = [C.c_void_p, C.c_int, D, C.c_int, C.c_int, C.POINTER(C.c_int)]
-    for f in ("mpmref_compute_mu_lam", "mpmref_compute_mass", "mpmref_compute_cov_from_F"):
+    for f in ("mpmref_compute_mu_lam", "mpmref_compute_mass", "mpmref_compute_cov_from_F", "mpmref_compute_bulk",
+              "mpmref_compute_R_from_F"):
         getattr(lib, f).argtypes = [C.c_void_p]
     lib.mpmref_svd3.argtypes = [D, D, D, D]
+    lib.mpmref_apply_additional_params.argtypes = [C.c_void_p, D]
+    lib.mpmref_select_box.argtypes = [C.c_void_p, D, D, C.POINTER(C.c_int)]
+    lib.mpmref_select_cylinder.argtypes = [C.c_void_p, D, D, C.c_double, C.c_double, C.POINTER(C.c_int)]
     lib.mpmref_stress_of_F.argtypes = [C.c_void_p, C.c_int]
     lib.mpmref_step.argtypes = [C.c_void_p, C.c_int, C.c_double]
     lib.mpmref_num_threads.restype = C.c_int
@@ -158,6 +163,28 @@ class MpmRef:
 
     def compute_cov_from_F(self):
         self.lib.mpmref_compute_cov_from_F(self.h)
+
+    def compute_bulk(self):
+        self.lib.mpmref_compute_bulk(self.h)
+
+    def compute_R_from_F(self):
+        self.lib.mpmref_compute_R_from_F(self.h)
+
+    def apply_additional_params(self, point, size, E, nu, density, material):
+        box = np.array(list(point) + list(size) + [E, nu, density, material], dtype=np.float64)
+        self.lib.mpmref_apply_additional_params(self.h, _dp(box))
+
+    def select_box(self, point, size) -> np.ndarray:
+        mask = np.zeros(self.n, dtype=np.int32)
+        self.lib.mpmref_select_box(self.h, _dp(np.asarray(point, dtype=np.float64)), _dp(np.asarray(size, dtype=np.float64)),
+                                   mask.ctypes.data_as(C.POINTER(C.c_int)))
+        return mask
+
+    def select_cylinder(self, point, normal, half_height, radius) -> np.ndarray:
+        mask = np.zeros(self.n, dtype=np.int32)
+        self.lib.mpmref_select_cylinder(self.h, _dp(np.asarray(point, dtype=np.float64)), _dp(np.asarray(normal, dtype=np.float64)),
+                                        float(half_height), float(radius), mask.ctypes.data_as(C.POINTER(C.c_int)))
+        return mask
 
     def stress_of(self, p: int):
         self.lib.mpmref_stress_of_F(self.h, p)
