@@ -4,8 +4,9 @@
   render_frame_transform     third_party/PhysGaussian/gs_simulation.py:591-600 with utils/transformation_utils.py:19-20
                              (undotransform2origin), :57-87 (cov helpers), :101-126 (undoshift2center111, inverse rotations)
 
-PARITY UNPINNED: taichi is not installable here and transformation_utils hard-codes device="cuda"; the reference has no tests
-for these. Pinned by hand-computed cases in tests/test_frame_export.py. Only tests/ may import this file.
+PINNED BY THE REFERENCE'S OWN FUNCTIONS: tests/golden/make_transfer_golden.py executes the reference's Taichi kernels on a
+minimal float32 `ti` stand-in and its transformation_utils functions on CPU torch (the device="cuda" literals dropped);
+tests/test_transfer_golden.py compares against that fixture (volume bit-exact, transforms to 2e-6). Only tests/ may import this file.
 """
 import numpy as np
 

@@ -7,15 +7,17 @@ transfer, following the reference line by line with numpy / scikit-learn as the 
                                 third_party/PhysGaussian/material_field.py:26-86, 228-293
   apply_additional_params       third_party/PhysGaussian/mpm_solver_warp/mpm_utils.py:591-610 via material_field.py:343-363
 
-PARITY UNPINNED: the reference modules import hydra / plyfile / warp / taichi (absent here), so they cannot be imported to
-generate golden vectors, and the reference has no tests for this path. The functions below are pinned by hand-computed
-cases in tests/test_material_transfer.py only. Only tests/ may import this file.
+PINNED BY THE REFERENCE'S OWN FUNCTIONS: the reference modules import hydra / plyfile / warp / taichi (absent here) and cannot be
+imported whole, but tests/golden/make_transfer_golden.py pulls the function sources out of the reference files with `ast` and
+executes them (real numpy / scikit-learn / torch); tests/test_transfer_golden.py holds every function below to the resulting
+fixture tests/golden/transfer_golden.npz BIT-EXACTLY (that is how the DEFAULT_VALUES['E'] = 5000.0 slip of round 1 was caught).
+Only tests/ may import this file.
 """
 from __future__ import annotations
 
 import numpy as np
 
-DEFAULT_VALUES = {"density": 1000.0, "E": 1e6, "nu": 0.3, "part_label": 0, "material_id": "stationary"}   # material_field.py:16-23
+DEFAULT_VALUES = {"density": 1000.0, "E": 5000.0, "nu": 0.3, "part_label": 0, "material_id": "stationary"}   # material_field.py:16-23
 STATIONARY_ID = 6                                                                                       # mpm_solver_warp.py:10-26
 
 

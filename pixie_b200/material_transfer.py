@@ -25,7 +25,7 @@ from .mpm_solver_warp import get_material_name
 #: normalization_stats/normalization_ranges.yaml p1/p99 (config keys training.{density,E,nu}_{min,max})
 DEFAULT_RANGES = dict(density_min=1.703, density_max=3.871, E_min=3.018, E_max=10.882, nu_min=0.2103, nu_max=0.4493)
 #: material_field.py:16-23
-DEFAULT_VALUES = {"density": 1000.0, "E": 1e6, "nu": 0.3, "part_label": 0, "material_id": "stationary"}
+DEFAULT_VALUES = {"density": 1000.0, "E": 5000.0, "nu": 0.3, "part_label": 0, "material_id": "stationary"}
 
 
 def _stream(dev):
