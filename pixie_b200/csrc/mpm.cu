@@ -2,15 +2,18 @@
 // (third_party/PhysGaussian/mpm_solver_warp/mpm_solver_warp.py:514-637) and the Warp kernels it
 // launches (mpm_utils.py:295-588, BC closures mpm_solver_warp.py:785-1179).
 //
-// One substep = three launches, no host synchronisation:
-//   mpm_p2g   : [impulse / Dirichlet particle BCs] -> return mapping + Kirchhoff stress -> scatter
-//               (one red.global.add.v4.f32 per node: grid node = float4 {mv.xyz, m})
-//   mpm_grid  : normalise + gravity + damping + every grid BC (from a device BC table, registration
-//               order) -> grid_v; clears the {mv, m} node it just consumed (zero_grid fused away)
-//   mpm_g2p   : gather, x/v/C/F_trial update, optional covariance update; thread 0 advances the
-//               simulation clock and moves the cuboid colliders (the reference's host-side
-//               `modify`, mpm_solver_warp.py:899-905, and `self.time += dt`, :637)
-// Substeps are replayed from a CUDA graph.
+// Two paths:
+//   default ("fused", mpm_fused.cuh): a private cell-sorted SoA copy of the particle state and two launches per
+//     substep (particle kernel: g2p(i) + BCs/stress/p2g(i+1); grid kernel over the particles' node box), replayed from
+//     a CUDA graph of 50 substeps with the simulation clock on the device;
+//   direct (this file; slab-decomposed runs, PIXIE_MPM_DIRECT=1): four launches per substep on the caller's arrays
+//     mpm_stress  : [impulse / Dirichlet particle BCs] -> return mapping + Kirchhoff stress
+//     mpm_scatter : warp-aggregated p2g (one red.global.add.v4.f32 per run and node: grid node = float4 {mv.xyz, m})
+//     mpm_grid    : normalise + gravity + damping + every grid BC (from a device BC table, registration
+//                   order) -> grid_v; clears the {mv, m} node it just consumed (zero_grid fused away)
+//     mpm_g2p     : gather, x/v/C/F_trial update, optional covariance update; thread 0 advances the
+//                   simulation clock and moves the cuboid colliders (the reference's host-side
+//                   `modify`, mpm_solver_warp.py:899-905, and `self.time += dt`, :637)
 #include "mpm.cuh"
 #include "mpm_math.cuh"
 #include "ptx.cuh"
@@ -503,7 +506,7 @@ __global__ void mpm_select_cyl_kernel(const DevState s, float3 point, float3 nor
     mask[p] = (vd < half_height && hd < radius) ? 1 : 0;
 }
 
-#include "mpm_tiled.cuh"
+#include "mpm_fused.cuh"
 
 // base-cell key of every live particle (+ identity index), input of the radix sort that produces DevState::order
 __global__ void mpm_cell_key_kernel(const float* __restrict__ x, int n, float inv_dx, int n_grid, int* __restrict__ keys, int* __restrict__ idx) {
@@ -527,46 +530,42 @@ struct Mpm {
     void* fields[PIXIE_MPM_FIELD_COUNT] = {nullptr};
     pixie_mpm_params params{};
     std::vector<DevBC> bcs;
-    bool bcs_dirty = true;
     float4* grid_mv = nullptr;
     float4* grid_v = nullptr;
-    double* d_time = nullptr;
+    double* d_time = nullptr;          // direct path clock
     DevBC* d_bcs = nullptr;
-    // CUDA graph of kGraphSteps substeps, keyed by dt and the state snapshot it was captured with
+    // CUDA graph of a batch of substeps, keyed by dt and the state snapshot it was captured with
     cudaGraphExec_t graph = nullptr;
     double graph_dt = 0;
     bool graph_valid = false;
+    int graph_parity = 0;
     std::string error;
 
-    // ---- cell order for the warp-aggregated scatter (three-kernel path)
+    // ---- cell order (radix sort of base-cell keys): indirection of the direct path, physical order of the fused path
     int *cell_order = nullptr, *cell_keys = nullptr, *cell_keys_sorted = nullptr, *cell_idx = nullptr;
     void* cub_tmp = nullptr;
     size_t cub_bytes = 0;
     bool order_valid = false;
     int steps_since_order = 0;
 
-    // ---- tiled path (mpm_tiled.cuh)
-    bool tiled = true;
-    struct SortBuf {
-        float *x = nullptr, *v = nullptr, *C = nullptr, *F = nullptr, *Ft = nullptr, *stress = nullptr;
-        float *mass = nullptr, *vol = nullptr, *mu = nullptr, *lam = nullptr, *bulk = nullptr, *ys = nullptr;
-        int *material = nullptr, *selection = nullptr, *perm = nullptr;
-    } sb[2];
-    int cur = 0;                       // sb[cur] holds the live sorted state
-    int *keys = nullptr, *counts = nullptr, *off = nullptr, *cursor = nullptr, *occ = nullptr, *order = nullptr, *d_nocc = nullptr;
-    int nt = 0, ntiles = 0, n_occ = 0;
-    float4* mvbuf[3] = {nullptr, nullptr, nullptr};
-    int wbuf = 0;                      // buffer the next scatter writes (zero by invariant)
+    // ---- fused path (mpm_fused.cuh): private cell-sorted SoA copy of the particle state
+    bool fused = true;                 // false: four-kernel path on the caller's arrays (slab-decomposed runs, PIXIE_MPM_DIRECT=1)
+    struct FsBuf { float* f = nullptr; int *material = nullptr, *selection = nullptr, *perm = nullptr; } fs[2];
+    int cap = 0;
+    int* d_box = nullptr;              // [6] node box swept by the grid kernel
     double* tslots = nullptr;          // [2] clock, by substep parity
-    float* pts = nullptr;              // [2][kMaxBC][3] moving BC points, by substep parity
+    float* pts = nullptr;              // [2][kMaxBC][3] collider points (the cuboid ones move), by substep parity
     int tpar = 0;
     bool internal_valid = false;       // sorted state mirrors the caller's arrays (+ steps taken since)
     bool user_stale = false;           // sorted state is ahead of the caller's arrays
     int steps_since_sort = 0;
-    std::vector<void*> tiled_allocs;
+    int agg = 3;                       // log2 of the longest aggregated run in the scatter (PIXIE_MPM_AGG)
 };
 
-static constexpr int kGraphSteps = 25;
+static constexpr int kGraphSteps = 25;         // direct path
+static constexpr int kFusedGraphSteps = 50;    // fused path (even: the clock parity returns to where it started)
+static constexpr int kResortEvery = 100;       // substeps between re-sorts; CFL keeps a particle within ~a cell of its slot far longer
+static constexpr int kBoxMargin = 2;           // nodes added around the particles' node box at every sort
 
 static DevState make_state(Mpm* m) {
     DevState s{};
@@ -590,119 +589,119 @@ static DevState make_state(Mpm* m) {
     s.rpic_damping = q.rpic_damping; s.grid_v_damping_scale = q.grid_v_damping_scale; s.alpha = q.alpha;
     s.hardening = q.hardening; s.xi = q.xi; s.plastic_viscosity = q.plastic_viscosity; s.softening = q.softening;
     s.update_cov_with_F = q.update_cov_with_F;
-    s.scatter_slices = getenv("PIXIE_MPM_SLICES") ? atoi(getenv("PIXIE_MPM_SLICES")) : 1;   // r01 A/B at 1e5 particles: 47.4 us (1) vs 51.1 us (3) per substep
+    s.scatter_slices = 1;
     return s;
 }
 
 void mpm_destroy(Mpm* m);
 int mpm_sync(Mpm* m, cudaStream_t st);
 
-// ---------------------------------------------------------------------------------- tiled path: host
-static constexpr int kResortEvery = 32;    // substeps between re-sorts (CFL keeps drift << one cell)
-
-template <typename T>
-static bool talloc(Mpm* m, T** p, size_t n) {
-    if (cudaMalloc(p, n * sizeof(T)) != cudaSuccess) return false;
-    cudaMemset(*p, 0, n * sizeof(T));
-    m->tiled_allocs.push_back(*p);
-    return true;
-}
-
-static int tiled_alloc_grid(Mpm* m) {
-    const size_t nodes = (size_t)m->n_grid * m->n_grid * m->n_grid;
-    m->nt = (m->n_grid + kTile - 1) / kTile;
-    m->ntiles = m->nt * m->nt * m->nt;
-    bool ok = true;
-    for (int i = 0; i < 3; ++i) ok = ok && talloc(m, &m->mvbuf[i], nodes);
-    ok = ok && talloc(m, &m->counts, (size_t)m->ntiles) && talloc(m, &m->off, (size_t)m->ntiles + 1) &&
-         talloc(m, &m->cursor, (size_t)m->ntiles) && talloc(m, &m->occ, (size_t)m->ntiles);
-    m->wbuf = 0;
-    return ok ? 0 : 1;
-}
-
-static int tiled_alloc(Mpm* m) {
-    const size_t n = (size_t)m->n;
-    bool ok = true;
-    for (int b = 0; b < 2; ++b) {
-        Mpm::SortBuf& s = m->sb[b];
-        ok = ok && talloc(m, &s.x, 3 * n) && talloc(m, &s.v, 3 * n) && talloc(m, &s.C, 9 * n) && talloc(m, &s.F, 9 * n) &&
-             talloc(m, &s.Ft, 9 * n) && talloc(m, &s.stress, 9 * n) && talloc(m, &s.mass, n) && talloc(m, &s.vol, n) &&
-             talloc(m, &s.mu, n) && talloc(m, &s.lam, n) && talloc(m, &s.bulk, n) && talloc(m, &s.ys, n) &&
-             talloc(m, &s.material, n) && talloc(m, &s.selection, n) && talloc(m, &s.perm, n);
+// ---------------------------------------------------------------------------------- sort scratch (both paths)
+static int sort_alloc(Mpm* m) {
+    if (m->cell_order) return 0;
+    const size_t cap = (size_t)m->n;
+    if (cudaMalloc(&m->cell_order, cap * sizeof(int)) != cudaSuccess || cudaMalloc(&m->cell_keys, cap * sizeof(int)) != cudaSuccess ||
+        cudaMalloc(&m->cell_keys_sorted, cap * sizeof(int)) != cudaSuccess || cudaMalloc(&m->cell_idx, cap * sizeof(int)) != cudaSuccess) {
+        m->error = "cudaMalloc failed (cell order)"; return 1;
     }
-    ok = ok && talloc(m, &m->keys, n) && talloc(m, &m->order, n) && talloc(m, &m->d_nocc, (size_t)1) &&
-         talloc(m, &m->tslots, (size_t)2) && talloc(m, &m->pts, (size_t)2 * kMaxBC * 3);
-    if (!ok) return 1;
-    return tiled_alloc_grid(m);
+    cub::DeviceRadixSort::SortPairs(nullptr, m->cub_bytes, m->cell_keys, m->cell_keys_sorted, m->cell_idx, m->cell_order, (int)cap, 0, 32, 0);
+    if (cudaMalloc(&m->cub_tmp, m->cub_bytes) != cudaSuccess) { m->error = "cudaMalloc failed (sort scratch)"; return 1; }
+    return 0;
+}
+static int key_bits(const Mpm* m) {
+    int bits = 1;
+    while ((1ll << bits) < (long long)m->n_grid * m->n_grid * m->n_grid) ++bits;
+    return bits;
 }
 
-// Builds the tile lists from positions `x` (n particles) and fills `order` (new position -> old position).
-static int tiled_build_order(Mpm* m, const float* x, cudaStream_t st) {
+// ---------------------------------------------------------------------------------- fused path: host
+static FsUser fs_user(Mpm* m) {
+    FsUser u{};
+    auto f = [&](int id) { return reinterpret_cast<float*>(m->fields[id]); };
+    u.x = f(PIXIE_MPM_X); u.v = f(PIXIE_MPM_V); u.C = f(PIXIE_MPM_C); u.F = f(PIXIE_MPM_F); u.Ft = f(PIXIE_MPM_F_TRIAL);
+    u.stress = f(PIXIE_MPM_STRESS); u.mass = f(PIXIE_MPM_MASS); u.vol = f(PIXIE_MPM_VOL); u.mu = f(PIXIE_MPM_MU); u.lam = f(PIXIE_MPM_LAM);
+    u.bulk = f(PIXIE_MPM_BULK); u.ys = f(PIXIE_MPM_YIELD); u.cov = f(PIXIE_MPM_COV);
+    u.material = reinterpret_cast<int*>(m->fields[PIXIE_MPM_MATERIAL]);
+    u.selection = reinterpret_cast<int*>(m->fields[PIXIE_MPM_SELECTION]);
+    return u;
+}
+
+static int fused_alloc(Mpm* m) {
+    if (m->fs[0].f) return 0;
+    m->cap = (m->n + 31) / 32 * 32;
+    const size_t cap = (size_t)m->cap;
+    bool ok = true;
+    for (int b = 0; b < 2 && ok; ++b) {
+        Mpm::FsBuf& s = m->fs[b];
+        ok = cudaMalloc(&s.f, (size_t)FS_NFLOAT * cap * sizeof(float)) == cudaSuccess && cudaMalloc(&s.material, cap * sizeof(int)) == cudaSuccess &&
+             cudaMalloc(&s.selection, cap * sizeof(int)) == cudaSuccess && cudaMalloc(&s.perm, cap * sizeof(int)) == cudaSuccess;
+        if (ok) {
+            cudaMemset(s.f, 0, (size_t)FS_NFLOAT * cap * sizeof(float));
+            cudaMemset(s.material, 0, cap * sizeof(int)); cudaMemset(s.selection, 0, cap * sizeof(int)); cudaMemset(s.perm, 0, cap * sizeof(int));
+        }
+    }
+    if (!ok) { m->error = "cudaMalloc failed (sorted particle state)"; return 1; }
+    return sort_alloc(m);
+}
+
+// node box of the particles at `x` (+ margin) into m->d_box
+static void fused_box(Mpm* m, const float* x, long long stride_comp, long long stride_part, cudaStream_t st) {
+    const int init[6] = {m->n_grid, m->n_grid, m->n_grid, 0, 0, 0};
+    cudaMemcpyAsync(m->d_box, init, sizeof(init), cudaMemcpyHostToDevice, st);
     const float inv_dx = (float)((double)m->n_grid / (double)m->grid_lim);
-    cudaMemsetAsync(m->counts, 0, (size_t)m->ntiles * sizeof(int), st);
-    tiled_count_kernel<<<(m->n + 255) / 256, 256, 0, st>>>(x, m->n, inv_dx, m->n_grid, m->nt, m->keys, m->counts);
-    tiled_scan_kernel<<<1, 1024, 0, st>>>(m->counts, m->ntiles, m->off, m->cursor, m->occ, m->d_nocc);
-    tiled_place_kernel<<<(m->n + 255) / 256, 256, 0, st>>>(m->keys, m->n, m->cursor, m->order);
-    if (cudaMemcpyAsync(&m->n_occ, m->d_nocc, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess) return 1;
-    if (cudaStreamSynchronize(st) != cudaSuccess) return 1;
+    fs_box_kernel<<<148, 256, 0, st>>>(x, stride_comp, stride_part, m->n, inv_dx, m->n_grid, kBoxMargin, m->d_box, 0);
+    fs_box_kernel<<<1, 32, 0, st>>>(x, stride_comp, stride_part, m->n, inv_dx, m->n_grid, kBoxMargin, m->d_box, 1);
+}
+
+static int fused_sort(Mpm* m, const float* x, long long stride_comp, long long stride_part, cudaStream_t st) {
+    const float inv_dx = (float)((double)m->n_grid / (double)m->grid_lim);
+    fs_key_kernel<<<(m->n + 255) / 256, 256, 0, st>>>(x, stride_comp, stride_part, m->n, inv_dx, m->n_grid, m->cell_keys, m->cell_idx);
+    size_t bytes = m->cub_bytes;
+    if (cub::DeviceRadixSort::SortPairs(m->cub_tmp, bytes, m->cell_keys, m->cell_keys_sorted, m->cell_idx, m->cell_order, m->n, 0, key_bits(m), st) != cudaSuccess) {
+        m->error = "radix sort failed"; return 1;
+    }
     m->steps_since_sort = 0;
     return 0;
 }
 
-static PermuteArgs permute_dst(Mpm* m, int b, PermuteArgs a) {
-    Mpm::SortBuf& d = m->sb[b];
-    a.ox = d.x; a.ov = d.v; a.oC = d.C; a.oF = d.F; a.oFt = d.Ft; a.ostress = d.stress; a.omass = d.mass; a.ovol = d.vol;
-    a.omu = d.mu; a.olam = d.lam; a.obulk = d.bulk; a.oys = d.ys; a.omaterial = d.material; a.oselection = d.selection; a.operm = d.perm;
-    return a;
-}
-
 // caller's arrays -> sorted state
-static int tiled_gather_from_user(Mpm* m, cudaStream_t st) {
-    auto f = [&](int id) { return reinterpret_cast<const float*>(m->fields[id]); };
-    if (tiled_build_order(m, f(PIXIE_MPM_X), st)) { m->error = "tile sort failed"; return 1; }
-    PermuteArgs a{};
-    a.order = m->order; a.n = m->n;
-    a.x = f(PIXIE_MPM_X); a.v = f(PIXIE_MPM_V); a.C = f(PIXIE_MPM_C); a.F = f(PIXIE_MPM_F); a.Ft = f(PIXIE_MPM_F_TRIAL);
-    a.stress = f(PIXIE_MPM_STRESS); a.mass = f(PIXIE_MPM_MASS); a.vol = f(PIXIE_MPM_VOL); a.mu = f(PIXIE_MPM_MU); a.lam = f(PIXIE_MPM_LAM);
-    a.bulk = f(PIXIE_MPM_BULK); a.ys = f(PIXIE_MPM_YIELD);
-    a.material = reinterpret_cast<const int*>(m->fields[PIXIE_MPM_MATERIAL]);
-    a.selection = reinterpret_cast<const int*>(m->fields[PIXIE_MPM_SELECTION]);
-    a.perm_src = nullptr;
-    m->cur = 0;
-    a = permute_dst(m, 0, a);
-    tiled_permute_kernel<<<(m->n + 255) / 256, 256, 0, st>>>(a);
+static int fused_gather_from_user(Mpm* m, cudaStream_t st) {
+    if (fused_alloc(m)) return 1;
+    const FsUser u = fs_user(m);
+    if (fused_sort(m, u.x, 1, 3, st)) return 1;
+    Mpm::FsBuf& d = m->fs[0];
+    fs_gather_kernel<<<(m->n + 255) / 256, 256, 0, st>>>(u, m->cell_order, m->n, m->cap, d.f, d.material, d.selection, d.perm,
+                                                          m->params.update_cov_with_F ? 1 : 0);
+    fused_box(m, u.x, 1, 3, st);
     m->internal_valid = true;
     m->user_stale = false;
     return cudaGetLastError() != cudaSuccess;
 }
 
-// re-sort the live sorted state (between two fused launches)
-static int tiled_resort(Mpm* m, cudaStream_t st) {
-    const Mpm::SortBuf& s = m->sb[m->cur];
-    if (tiled_build_order(m, s.x, st)) { m->error = "tile sort failed"; return 1; }
-    PermuteArgs a{};
-    a.order = m->order; a.n = m->n;
-    a.x = s.x; a.v = s.v; a.C = s.C; a.F = s.F; a.Ft = s.Ft; a.stress = s.stress; a.mass = s.mass; a.vol = s.vol; a.mu = s.mu;
-    a.lam = s.lam; a.bulk = s.bulk; a.ys = s.ys; a.material = s.material; a.selection = s.selection; a.perm_src = s.perm;
-    a = permute_dst(m, m->cur ^ 1, a);
-    tiled_permute_kernel<<<(m->n + 255) / 256, 256, 0, st>>>(a);
-    m->cur ^= 1;
+// re-sort of the live sorted state (between two launches of the particle kernel)
+static int fused_resort(Mpm* m, cudaStream_t st) {
+    Mpm::FsBuf& a = m->fs[0];
+    Mpm::FsBuf& b = m->fs[1];
+    if (fused_sort(m, a.f + (size_t)FS_X * m->cap, m->cap, 1, st)) return 1;
+    fs_permute_kernel<<<(m->n + 255) / 256, 256, 0, st>>>(a.f, a.material, a.selection, a.perm, m->cell_order, m->n, m->cap, b.f, b.material,
+                                                           b.selection, b.perm);
+    // back into buffer 0: the captured graph and the launch arguments keep pointing at it
+    const size_t cap = (size_t)m->cap;
+    cudaMemcpyAsync(a.f, b.f, (size_t)FS_NFLOAT * cap * sizeof(float), cudaMemcpyDeviceToDevice, st);
+    cudaMemcpyAsync(a.material, b.material, cap * sizeof(int), cudaMemcpyDeviceToDevice, st);
+    cudaMemcpyAsync(a.selection, b.selection, cap * sizeof(int), cudaMemcpyDeviceToDevice, st);
+    cudaMemcpyAsync(a.perm, b.perm, cap * sizeof(int), cudaMemcpyDeviceToDevice, st);
+    fused_box(m, a.f + (size_t)FS_X * m->cap, m->cap, 1, st);
     return cudaGetLastError() != cudaSuccess;
 }
 
-// sorted state -> caller's arrays (if it is ahead); afterwards the caller may mutate its arrays, so the
-// sorted copy is considered out of date.
+// sorted state -> caller's arrays (if it is ahead); afterwards the caller may mutate its arrays, so the sorted copy is
+// considered out of date.
 int mpm_sync(Mpm* m, cudaStream_t st) {
-    if (!m->tiled) return 0;
+    if (!m->fused) return 0;
     if (m->user_stale) {
-        const Mpm::SortBuf& s = m->sb[m->cur];
-        auto f = [&](int id) { return reinterpret_cast<float*>(m->fields[id]); };
-        UnsortArgs a{};
-        a.perm = s.perm; a.n = m->n;
-        a.x = s.x; a.v = s.v; a.C = s.C; a.F = s.F; a.Ft = s.Ft; a.stress = s.stress; a.mu = s.mu; a.lam = s.lam; a.ys = s.ys;
-        a.ox = f(PIXIE_MPM_X); a.ov = f(PIXIE_MPM_V); a.oC = f(PIXIE_MPM_C); a.oF = f(PIXIE_MPM_F); a.oFt = f(PIXIE_MPM_F_TRIAL);
-        a.ostress = f(PIXIE_MPM_STRESS); a.omu = f(PIXIE_MPM_MU); a.olam = f(PIXIE_MPM_LAM); a.oys = f(PIXIE_MPM_YIELD);
-        tiled_unsort_kernel<<<(m->n + 255) / 256, 256, 0, st>>>(a);
+        const Mpm::FsBuf& s = m->fs[0];
+        fs_unsort_kernel<<<(m->n + 255) / 256, 256, 0, st>>>(fs_user(m), s.perm, m->n, m->cap, s.f, m->params.update_cov_with_F ? 1 : 0);
         m->user_stale = false;
         if (cudaGetLastError() != cudaSuccess) { m->error = "unsort launch failed"; return 1; }
     }
@@ -710,54 +709,125 @@ int mpm_sync(Mpm* m, cudaStream_t st) {
     return 0;
 }
 
-static TiledState tiled_state(Mpm* m) {
-    TiledState t{};
-    Mpm::SortBuf& s = m->sb[m->cur];
-    t.x = s.x; t.v = s.v; t.C = s.C; t.F = s.F; t.Ft = s.Ft; t.stress = s.stress; t.mass = s.mass; t.vol = s.vol; t.mu = s.mu; t.lam = s.lam;
-    t.bulk = s.bulk; t.yield_stress = s.ys; t.material = s.material; t.selection = s.selection; t.perm = s.perm;
-    t.occ = m->occ; t.tile_off = m->off; t.nt = m->nt;
+static FusedState fused_state(Mpm* m) {
+    FusedState t{};
+    const Mpm::FsBuf& s = m->fs[0];
+    t.f = s.f; t.material = s.material; t.selection = s.selection; t.perm = s.perm;
+    t.cap = m->cap; t.n = m->n;
+    t.grid_v = m->grid_v; t.grid_mv = m->grid_mv; t.box = m->d_box;
     t.bcs = m->d_bcs; t.n_bc = (int)m->bcs.size();
-    t.n = m->n; t.n_grid = m->n_grid;
+    t.n_particle_bc = 0;
+    for (const DevBC& b : m->bcs) t.n_particle_bc += b.kind >= PIXIE_BC_IMPULSE ? 1 : 0;
+    t.n_grid = m->n_grid;
     t.dx = (float)((double)m->grid_lim / (double)m->n_grid);
     t.inv_dx = (float)((double)m->n_grid / (double)m->grid_lim);
     const pixie_mpm_params& q = m->params;
-    t.gx = q.gravity[0]; t.gy = q.gravity[1]; t.gz = q.gravity[2];
-    t.rpic_damping = q.rpic_damping; t.grid_v_damping_scale = q.grid_v_damping_scale; t.alpha = q.alpha; t.hardening = q.hardening;
-    t.xi = q.xi; t.plastic_viscosity = q.plastic_viscosity; t.softening = q.softening;
+    t.rpic_damping = q.rpic_damping; t.alpha = q.alpha; t.hardening = q.hardening; t.xi = q.xi;
+    t.plastic_viscosity = q.plastic_viscosity; t.softening = q.softening;
+    t.update_cov_with_F = q.update_cov_with_F;
     return t;
 }
 
-static void tiled_launch(Mpm* m, bool do_g2p, bool do_p2g, bool write_all, float dt, double dt_d, cudaStream_t st) {
-    TiledState t = tiled_state(m);
+static void fused_launch(Mpm* m, bool do_g2p, bool do_p2g, bool write_all, float dt, cudaStream_t st) {
+    FusedState t = fused_state(m);
     t.do_g2p = do_g2p; t.do_p2g = do_p2g; t.write_all = write_all;
-    // three rotating grid buffers; invariant: mvbuf[wbuf] is zero. Every launch reads the scatter completed by
-    // the previous scattering launch ((wbuf+2)%3), scatters into wbuf and clears the third buffer, which the
-    // launch before it read and which becomes the scatter target after this one.
-    t.mv_read = m->mvbuf[(m->wbuf + 2) % 3];
-    t.mv_write = m->mvbuf[m->wbuf];
-    t.mv_clear = m->mvbuf[(m->wbuf + 1) % 3];
-    t.time_in = m->tslots + m->tpar; t.time_out = m->tslots + (m->tpar ^ 1);
-    t.pts_in = m->pts + (size_t)m->tpar * kMaxBC * 3; t.pts_out = m->pts + (size_t)(m->tpar ^ 1) * kMaxBC * 3;
-    mpm_tiled_kernel<<<m->n_occ, kTiledThreads, 0, st>>>(t, dt, dt_d);
-    if (do_p2g) m->wbuf = (m->wbuf + 1) % 3;        // this launch filled wbuf; the next scatter goes to the buffer it cleared
-    if (do_g2p) m->tpar ^= 1;
+    t.time = m->tslots + m->tpar;                 // clock of the substep whose stress / scatter runs in this launch
+    const int blocks = (m->n + kFusedThreads - 1) / kFusedThreads;
+    switch (m->agg) {
+        case 0: mpm_fused_kernel<0><<<blocks, kFusedThreads, 0, st>>>(t, dt); break;
+        case 1: mpm_fused_kernel<1><<<blocks, kFusedThreads, 0, st>>>(t, dt); break;
+        case 2: mpm_fused_kernel<2><<<blocks, kFusedThreads, 0, st>>>(t, dt); break;
+        default: mpm_fused_kernel<3><<<blocks, kFusedThreads, 0, st>>>(t, dt); break;
+    }
 }
 
-static int mpm_step_tiled(Mpm* m, int n_substeps, double dt_d, cudaStream_t st) {
-    const float dt = (float)dt_d;
-    if (!m->internal_valid && tiled_gather_from_user(m, st)) return 1;
-    // prologue: scatter of the first substep (reads v, C, F_trial of the sorted state)
-    tiled_launch(m, false, true, n_substeps == 1, dt, dt_d, st);
-    for (int i = 0; i + 1 < n_substeps; ++i) {
-        if (m->steps_since_sort >= kResortEvery && tiled_resort(m, st)) return 1;
-        tiled_launch(m, true, true, i + 2 == n_substeps, dt, dt_d, st);    // g2p(i) + p2g(i+1)
-        ++m->steps_since_sort;
+static void gridbox_launch(Mpm* m, float dt, double dt_d, cudaStream_t st) {
+    GridBoxArgs g{};
+    g.grid_mv = m->grid_mv; g.grid_v = m->grid_v; g.box = m->d_box;
+    g.time_in = m->tslots + m->tpar; g.time_out = m->tslots + (m->tpar ^ 1);
+    g.pts_in = m->pts + (size_t)m->tpar * kMaxBC * 3; g.pts_out = m->pts + (size_t)(m->tpar ^ 1) * kMaxBC * 3;
+    g.bcs = m->d_bcs; g.n_bc = (int)m->bcs.size();
+    g.n_grid = m->n_grid; g.x_begin = m->x_begin; g.x_end = m->x_end;
+    g.dx = (float)((double)m->grid_lim / (double)m->n_grid);
+    const pixie_mpm_params& q = m->params;
+    g.gx = q.gravity[0]; g.gy = q.gravity[1]; g.gz = q.gravity[2]; g.grid_v_damping_scale = q.grid_v_damping_scale;
+    // enough blocks for two per SM; the kernel strides over the (usually much smaller than n_grid^3) node box
+    mpm_gridbox_kernel<<<296, 256, 0, st>>>(g, dt, dt_d);
+    m->tpar ^= 1;
+}
+
+// `count` substeps as: scatter(0) | grid(0) | g2p(0)+scatter(1) | ... | grid(count-1) | g2p(count-1)
+static void fused_batch(Mpm* m, int count, float dt, double dt_d, cudaStream_t st) {
+    fused_launch(m, false, true, count == 1, dt, st);
+    for (int i = 0; i < count; ++i) {
+        gridbox_launch(m, dt, dt_d, st);
+        if (i + 1 < count) fused_launch(m, true, true, i + 2 == count, dt, st);
+        else fused_launch(m, true, false, true, dt, st);
     }
-    tiled_launch(m, true, false, true, dt, dt_d, st);                       // g2p of the last substep
-    ++m->steps_since_sort;
+}
+
+static int mpm_step_fused(Mpm* m, int n_substeps, double dt_d, cudaStream_t st) {
+    const float dt = (float)dt_d;
+    if (!m->internal_valid && fused_gather_from_user(m, st)) return 1;
+    int done = 0;
+    if (n_substeps >= kFusedGraphSteps) {
+        if (!m->graph_valid || m->graph_dt != dt_d || m->graph_parity != m->tpar) {
+            if (m->graph) { cudaGraphExecDestroy(m->graph); m->graph = nullptr; }
+            cudaStream_t cs;
+            cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking);
+            cudaGraph_t g = nullptr;
+            const int par0 = m->tpar;
+            bool ok = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+            if (ok) {
+                fused_batch(m, kFusedGraphSteps, dt, dt_d, cs);
+                ok = cudaStreamEndCapture(cs, &g) == cudaSuccess && g;
+            }
+            m->tpar = par0;                                    // capture did not run anything
+            if (ok) ok = cudaGraphInstantiate(&m->graph, g, 0) == cudaSuccess;
+            if (g) cudaGraphDestroy(g);
+            cudaStreamDestroy(cs);
+            if (!ok) { cudaGetLastError(); m->graph = nullptr; }
+            m->graph_valid = ok;
+            m->graph_dt = dt_d;
+            m->graph_parity = par0;
+        }
+        while (m->graph_valid && n_substeps - done >= kFusedGraphSteps) {
+            if (m->steps_since_sort >= kResortEvery && fused_resort(m, st)) return 1;
+            if (cudaGraphLaunch(m->graph, st) != cudaSuccess) { m->error = "cudaGraphLaunch failed"; return 1; }
+            done += kFusedGraphSteps;                          // even number of substeps: the parity is back at graph_parity
+            m->steps_since_sort += kFusedGraphSteps;
+        }
+    }
+    while (done < n_substeps) {
+        if (m->steps_since_sort >= kResortEvery && fused_resort(m, st)) return 1;
+        const int count = std::min(n_substeps - done, kResortEvery);
+        fused_batch(m, count, dt, dt_d, st);
+        done += count;
+        m->steps_since_sort += count;
+    }
     m->user_stale = true;
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { m->error = std::string("kernel launch failed: ") + cudaGetErrorString(e); return 1; }
+    return 0;
+}
+
+// leave the fused path for good (slab-decomposed runs drive the four-kernel path on the caller's arrays)
+static int switch_to_direct(Mpm* m) {
+    if (!m->fused) return 0;
+    if (mpm_sync(m, 0)) return 1;
+    cudaDeviceSynchronize();
+    double t = 0;
+    cudaMemcpy(&t, m->tslots + m->tpar, sizeof(double), cudaMemcpyDeviceToHost);
+    cudaMemcpy(m->d_time, &t, sizeof(double), cudaMemcpyHostToDevice);
+    // moved collider points back into the BC table the direct kernels read
+    std::vector<float> pts((size_t)kMaxBC * 3);
+    cudaMemcpy(pts.data(), m->pts + (size_t)m->tpar * kMaxBC * 3, pts.size() * sizeof(float), cudaMemcpyDeviceToHost);
+    for (size_t k = 0; k < m->bcs.size(); ++k) {
+        for (int a = 0; a < 3; ++a) m->bcs[k].point[a] = pts[3 * k + a];
+        cudaMemcpy(m->d_bcs + k, &m->bcs[k], sizeof(DevBC), cudaMemcpyHostToDevice);
+    }
+    m->fused = false;
+    m->graph_valid = false;
     return 0;
 }
 
@@ -778,7 +848,10 @@ Mpm* mpm_create(int n_particles, int n_grid, float grid_lim, std::string& err) {
     if (cudaMalloc(&m->grid_mv, nodes * sizeof(float4)) != cudaSuccess ||
         cudaMalloc(&m->grid_v, nodes * sizeof(float4)) != cudaSuccess ||
         cudaMalloc(&m->d_time, sizeof(double)) != cudaSuccess ||
-        cudaMalloc(&m->d_bcs, kMaxBC * sizeof(DevBC)) != cudaSuccess) {
+        cudaMalloc(&m->d_bcs, kMaxBC * sizeof(DevBC)) != cudaSuccess ||
+        cudaMalloc(&m->d_box, 6 * sizeof(int)) != cudaSuccess ||
+        cudaMalloc(&m->tslots, 2 * sizeof(double)) != cudaSuccess ||
+        cudaMalloc(&m->pts, (size_t)2 * kMaxBC * 3 * sizeof(float)) != cudaSuccess) {
         err = "cudaMalloc failed (no CUDA device?)";
         delete m;
         return nullptr;
@@ -786,17 +859,18 @@ Mpm* mpm_create(int n_particles, int n_grid, float grid_lim, std::string& err) {
     cudaMemset(m->grid_mv, 0, nodes * sizeof(float4));
     cudaMemset(m->grid_v, 0, nodes * sizeof(float4));
     cudaMemset(m->d_time, 0, sizeof(double));
-    // The tiled single-launch path is opt-in: at 100k particles it is correct but latency-bound (113 us/substep vs
-    // 49 us for the three-kernel path).
-    m->tiled = getenv("PIXIE_MPM_TILED") != nullptr;
-    if (m->tiled && tiled_alloc(m)) { err = "cudaMalloc failed (tiled path)"; mpm_destroy(m); return nullptr; }
+    cudaMemset(m->tslots, 0, 2 * sizeof(double));
+    cudaMemset(m->pts, 0, (size_t)2 * kMaxBC * 3 * sizeof(float));
+    m->fused = getenv("PIXIE_MPM_DIRECT") == nullptr;
+    if (const char* a = getenv("PIXIE_MPM_AGG")) m->agg = std::min(3, std::max(0, atoi(a)));
     return m;
 }
 
 void mpm_destroy(Mpm* m) {
     if (!m) return;
     cudaFree(m->cell_order); cudaFree(m->cell_keys); cudaFree(m->cell_keys_sorted); cudaFree(m->cell_idx); cudaFree(m->cub_tmp);
-    for (void* p : m->tiled_allocs) cudaFree(p);
+    for (int b = 0; b < 2; ++b) { cudaFree(m->fs[b].f); cudaFree(m->fs[b].material); cudaFree(m->fs[b].selection); cudaFree(m->fs[b].perm); }
+    cudaFree(m->d_box); cudaFree(m->tslots); cudaFree(m->pts);
     if (m->graph) cudaGraphExecDestroy(m->graph);
     if (!m->grid_borrowed) cudaFree(m->grid_mv);
     cudaFree(m->grid_v); cudaFree(m->d_time); cudaFree(m->d_bcs);
@@ -807,20 +881,14 @@ int mpm_bind(Mpm* m, int field, void* ptr) {
     if (field < 0 || field >= PIXIE_MPM_FIELD_COUNT) { m->error = "bad field id"; return 1; }
     if (mpm_sync(m, 0)) return 1;          // flush results into the arrays bound so far before one of them changes
     m->fields[field] = ptr;
-    m->graph_valid = false;
+    m->graph_valid = m->fused ? m->graph_valid : false;   // the fused graph only references the private copy
     return 0;
 }
 int mpm_set_params(Mpm* m, const pixie_mpm_params& p) {
     if (mpm_sync(m, 0)) return 1;
-    if (p.n_grid != m->n_grid && m->tiled) {
-        // grid-sized tiled buffers are re-created with the grid (old ones are released with the handle)
-        const int old = m->n_grid;
-        m->n_grid = p.n_grid;
-        if (tiled_alloc_grid(m)) { m->n_grid = old; m->error = "cudaMalloc failed"; return 1; }
-        m->n_grid = old;
-    }
     if (p.n_grid != m->n_grid) {
         // set_parameters_dict re-allocates the grids when n_grid changes (mpm_solver_warp.py:318-343)
+        cudaDeviceSynchronize();
         cudaFree(m->grid_mv); cudaFree(m->grid_v);
         const size_t nodes = (size_t)p.n_grid * p.n_grid * p.n_grid;
         if (cudaMalloc(&m->grid_mv, nodes * sizeof(float4)) != cudaSuccess ||
@@ -836,7 +904,7 @@ int mpm_set_params(Mpm* m, const pixie_mpm_params& p) {
     return 0;
 }
 int mpm_add_bc(Mpm* m, const pixie_mpm_bc& b) {
-    if ((int)m->bcs.size() >= kMaxBC) { m->error = "too many boundary conditions"; return 1; }
+    if ((int)m->bcs.size() >= kMaxBC) { m->error = "too many boundary conditions (limit " + std::to_string(kMaxBC) + ")"; return 1; }
     if (b.kind >= PIXIE_BC_IMPULSE && !b.mask_dev) { m->error = "particle BC needs a mask"; return 1; }
     DevBC d{};
     d.kind = b.kind;
@@ -851,26 +919,22 @@ int mpm_add_bc(Mpm* m, const pixie_mpm_bc& b) {
     d.mask = b.mask_dev;
     if (mpm_sync(m, 0)) return 1;
     m->bcs.push_back(d);
-    // append in place: the device table also holds the *moved* cuboid positions of earlier BCs
-    cudaMemcpy(m->d_bcs + (m->bcs.size() - 1), &d, sizeof(DevBC), cudaMemcpyHostToDevice);
-    if (m->tiled) {
-        const size_t k = m->bcs.size() - 1;
-        cudaMemcpy(m->pts + 3 * k, d.point, 3 * sizeof(float), cudaMemcpyHostToDevice);
-        cudaMemcpy(m->pts + (size_t)kMaxBC * 3 + 3 * k, d.point, 3 * sizeof(float), cudaMemcpyHostToDevice);
-    }
+    // append in place: the device tables also hold the *moved* cuboid positions of earlier BCs
+    const size_t k = m->bcs.size() - 1;
+    cudaMemcpy(m->d_bcs + k, &d, sizeof(DevBC), cudaMemcpyHostToDevice);
+    cudaMemcpy(m->pts + 3 * k, d.point, 3 * sizeof(float), cudaMemcpyHostToDevice);
+    cudaMemcpy(m->pts + (size_t)kMaxBC * 3 + 3 * k, d.point, 3 * sizeof(float), cudaMemcpyHostToDevice);
     m->graph_valid = false;
     return 0;
 }
 int mpm_clear_bcs(Mpm* m) { m->bcs.clear(); m->graph_valid = false; return 0; }
 int mpm_set_time(Mpm* m, double t) {
-    if (m->tiled) {
-        const double both[2] = {t, t};
-        if (cudaMemcpy(m->tslots, both, sizeof(both), cudaMemcpyHostToDevice) != cudaSuccess) return 1;
-    }
+    const double both[2] = {t, t};
+    if (cudaMemcpy(m->tslots, both, sizeof(both), cudaMemcpyHostToDevice) != cudaSuccess) return 1;
     return cudaMemcpy(m->d_time, &t, sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess;
 }
 int mpm_get_time(Mpm* m, double* t) {
-    const double* src = (m->tiled && !m->params.update_cov_with_F) ? m->tslots + m->tpar : m->d_time;
+    const double* src = m->fused ? m->tslots + m->tpar : m->d_time;
     return cudaMemcpy(t, src, sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess;
 }
 
@@ -884,27 +948,17 @@ static int check_bound(Mpm* m) {
     return 0;
 }
 
-static constexpr int kReorderEvery = 100;   // substeps between re-sorts; CFL keeps a particle within ~a cell of its key for far longer
+static constexpr int kReorderEvery = 100;   // direct path: substeps between re-sorts of the order indirection
 
 // (Re)builds Mpm::cell_order from the current positions. Stream-ordered, no host sync: the graph reads the same buffer.
 static int mpm_build_cell_order(Mpm* m, cudaStream_t st) {
     const int n = m->n_active;
     if (n <= 0) { m->order_valid = false; return 0; }
-    int bits = 1;
-    while ((1ll << bits) < (long long)m->n_grid * m->n_grid * m->n_grid) ++bits;
-    if (!m->cell_order) {
-        const size_t cap = (size_t)m->n;
-        if (cudaMalloc(&m->cell_order, cap * sizeof(int)) != cudaSuccess || cudaMalloc(&m->cell_keys, cap * sizeof(int)) != cudaSuccess ||
-            cudaMalloc(&m->cell_keys_sorted, cap * sizeof(int)) != cudaSuccess || cudaMalloc(&m->cell_idx, cap * sizeof(int)) != cudaSuccess) {
-            m->error = "cudaMalloc failed (cell order)"; return 1;
-        }
-        cub::DeviceRadixSort::SortPairs(nullptr, m->cub_bytes, m->cell_keys, m->cell_keys_sorted, m->cell_idx, m->cell_order, (int)cap, 0, 32, st);
-        if (cudaMalloc(&m->cub_tmp, m->cub_bytes) != cudaSuccess) { m->error = "cudaMalloc failed (sort scratch)"; return 1; }
-    }
+    if (sort_alloc(m)) return 1;
     const float inv_dx = (float)((double)m->n_grid / (double)m->grid_lim);
     mpm_cell_key_kernel<<<(n + 255) / 256, 256, 0, st>>>(reinterpret_cast<const float*>(m->fields[PIXIE_MPM_X]), n, inv_dx, m->n_grid, m->cell_keys, m->cell_idx);
     size_t bytes = m->cub_bytes;
-    if (cub::DeviceRadixSort::SortPairs(m->cub_tmp, bytes, m->cell_keys, m->cell_keys_sorted, m->cell_idx, m->cell_order, n, 0, bits, st) != cudaSuccess) {
+    if (cub::DeviceRadixSort::SortPairs(m->cub_tmp, bytes, m->cell_keys, m->cell_keys_sorted, m->cell_idx, m->cell_order, n, 0, key_bits(m), st) != cudaSuccess) {
         m->error = "radix sort failed"; return 1;
     }
     m->steps_since_order = 0;
@@ -912,8 +966,7 @@ static int mpm_build_cell_order(Mpm* m, cudaStream_t st) {
     return 0;
 }
 
-// Threads per block of the per-particle kernels: 64 spreads 1e5 particles over the 148 SMs with a shorter tail than 128
-// (1563 vs 782 blocks); PIXIE_MPM_BLOCK overrides it for A/B runs.
+// Threads per block of the per-particle kernels of the direct path
 static int particle_block() {
     static const int b = getenv("PIXIE_MPM_BLOCK") ? atoi(getenv("PIXIE_MPM_BLOCK")) : 64;
     return (b == 32 || b == 64 || b == 128) ? b : 64;
@@ -925,8 +978,7 @@ static void launch_substep(const DevState& s, float dt, double dt_d, cudaStream_
     if (n > 0) {
         const int B = particle_block();
         mpm_stress_kernel<<<(n + B - 1) / B, B, 0, st>>>(s, dt);
-        if (s.scatter_slices == 3) mpm_scatter_kernel<3><<<dim3((n + B - 1) / B, 3), B, 0, st>>>(s, dt);
-        else mpm_scatter_kernel<1><<<(n + B - 1) / B, B, 0, st>>>(s, dt);
+        mpm_scatter_kernel<1><<<(n + B - 1) / B, B, 0, st>>>(s, dt);
     }
     mpm_grid_kernel<<<(unsigned)((nodes + 255) / 256), 256, 0, st>>>(s, dt);
     mpm_g2p_kernel<<<(std::max(n, 1) + particle_block() - 1) / particle_block(), particle_block(), 0, st>>>(s, dt, dt_d);
@@ -935,12 +987,7 @@ static void launch_substep(const DevState& s, float dt, double dt_d, cudaStream_
 int mpm_step(Mpm* m, int n_substeps, double dt_d, cudaStream_t st) {
     if (check_bound(m)) return 1;
     if (n_substeps <= 0) return 0;
-    if (m->tiled && !m->params.update_cov_with_F) return mpm_step_tiled(m, n_substeps, dt_d, st);
-    if (m->tiled) {   // covariance-updating runs use the three-kernel path on the caller's arrays
-        if (mpm_sync(m, st)) return 1;
-        double t = 0; cudaMemcpy(&t, m->tslots + m->tpar, sizeof(double), cudaMemcpyDeviceToHost);
-        cudaMemcpy(m->d_time, &t, sizeof(double), cudaMemcpyHostToDevice);
-    }
+    if (m->fused) return mpm_step_fused(m, n_substeps, dt_d, st);
     const float dt = (float)dt_d;
     if ((!m->order_valid || m->steps_since_order >= kReorderEvery) && mpm_build_cell_order(m, st)) return 1;
     const DevState s = make_state(m);
@@ -1023,7 +1070,7 @@ int mpm_select_cylinder(Mpm* m, const float* point, const float* normal, float h
 // ---- spatially sharded runs (BASELINE config 5): the caller owns the {mv,m} grid, exchanges ghost planes between
 //      scatter and finish, and migrates particles by shrinking / growing the live prefix of the bound arrays.
 int mpm_bind_grid(Mpm* m, void* mv4) {
-    if (m->tiled) { m->error = "bind_grid is not available on the tiled path"; return 1; }
+    if (switch_to_direct(m)) return 1;
     if (!m->grid_borrowed) cudaFree(m->grid_mv);
     m->grid_mv = reinterpret_cast<float4*>(mv4);
     m->grid_borrowed = true;
@@ -1032,32 +1079,32 @@ int mpm_bind_grid(Mpm* m, void* mv4) {
 }
 int mpm_set_slab(Mpm* m, int x_begin, int x_end) {
     if (x_begin < 0 || x_end > m->n_grid || x_begin >= x_end) { m->error = "bad slab range"; return 1; }
+    if (switch_to_direct(m)) return 1;
     m->x_begin = x_begin; m->x_end = x_end;
     m->graph_valid = false;
     return 0;
 }
 int mpm_set_active_count(Mpm* m, int n_active) {
     if (n_active < 0 || n_active > m->n) { m->error = "active count exceeds the bound capacity"; return 1; }
-    if (mpm_sync(m, 0)) return 1;
+    if (switch_to_direct(m)) return 1;
     m->n_active = n_active;
     m->order_valid = false;       // the order lists exactly the live prefix
     m->graph_valid = false;
     return 0;
 }
 int mpm_substep_scatter(Mpm* m, double dt_d, cudaStream_t st) {
-    if (m->tiled) { m->error = "split substeps are not available on the tiled path"; return 1; }
+    if (switch_to_direct(m)) return 1;
     if (check_bound(m)) return 1;
     const DevState s = make_state(m);
     if (s.n > 0) {
         const int B = particle_block();
         mpm_stress_kernel<<<(s.n + B - 1) / B, B, 0, st>>>(s, (float)dt_d);
-        if (s.scatter_slices == 3) mpm_scatter_kernel<3><<<dim3((s.n + B - 1) / B, 3), B, 0, st>>>(s, (float)dt_d);
-        else mpm_scatter_kernel<1><<<(s.n + B - 1) / B, B, 0, st>>>(s, (float)dt_d);
+        mpm_scatter_kernel<1><<<(s.n + B - 1) / B, B, 0, st>>>(s, (float)dt_d);
     }
     return cudaGetLastError() != cudaSuccess;
 }
 int mpm_substep_finish(Mpm* m, double dt_d, cudaStream_t st) {
-    if (m->tiled) { m->error = "split substeps are not available on the tiled path"; return 1; }
+    if (switch_to_direct(m)) return 1;
     if (check_bound(m)) return 1;
     const DevState s = make_state(m);
     const size_t nodes = (size_t)(s.x_end - s.x_begin) * s.n_grid * s.n_grid;

@@ -58,7 +58,8 @@ struct UNet {
     std::vector<double> op_flops;                         // algorithmic FLOPs per op (convs only)
     std::vector<std::unique_ptr<ConvOp>> convs;
     std::map<std::string, DevT> named;
-    int* d_err = nullptr;
+    int* d_err = nullptr;              // device view of h_err
+    volatile int* h_err = nullptr;     // mapped pinned host flag: a convolution that gave up waiting on its pipeline sets it
     double* d_stats = nullptr;
     size_t stats_doubles = 0, stats_cap = 0;
     int cur_nb = 1;
@@ -83,6 +84,7 @@ struct UNet {
         for (auto& g : graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
         for (auto& c : convs) conv_plan_destroy(c->plan);
         for (void* p : allocs) cudaFree(p);
+        if (h_err) cudaFreeHost(const_cast<int*>(h_err));
     }
 };
 
@@ -329,9 +331,14 @@ struct Builder {
     bool build() {
         const pixie_unet_config& c = u.cfg;
         const int G = c.grid_size;
-        if (cudaMalloc(&u.d_err, sizeof(int)) != cudaSuccess) return fail("cudaMalloc");
-        u.allocs.push_back(u.d_err);
-        cudaMemset(u.d_err, 0, sizeof(int));
+        {   // mapped pinned flag: the host can poll it without synchronising (checked at the start of every forward
+            // and after every synchronising call), the kernels write it through the device alias
+            int* h = nullptr;
+            if (cudaHostAlloc(&h, sizeof(int), cudaHostAllocMapped) != cudaSuccess) return fail("cudaHostAlloc");
+            *h = 0;
+            u.h_err = h;
+            if (cudaHostGetDevicePointer(&u.d_err, h, 0) != cudaSuccess) return fail("cudaHostGetDevicePointer");
+        }
         u.stats_cap = (size_t)NB * 2 * 64 * 1024;   // doubles; far above the ~70 norms x <=512 channels
         u.d_stats = dalloc<double>(u.stats_cap);
 
@@ -516,15 +523,20 @@ static int run_ops(UNet* u, int batch, const void* feat, float* out, cudaStream_
     return enqueue_ops(u, st);
 }
 
+// Non-blocking: reports (and re-arms) a pipeline timeout raised by any forward enqueued so far that has already run.
 static int check_err_flag(UNet* u) {
-    int h = 0;
-    cudaMemcpy(&h, u->d_err, sizeof(int), cudaMemcpyDeviceToHost);
-    if (h) { u->error = "conv pipeline timeout (device flag " + std::to_string(h) + ")"; return 1; }
+    const int h = u->h_err ? *u->h_err : 0;
+    if (h) {
+        *u->h_err = 0;
+        u->error = "conv pipeline timeout (device flag " + std::to_string(h) + "): the outputs of the affected forward are invalid";
+        return 1;
+    }
     return 0;
 }
 
 int unet_forward(UNet* u, const void* feat_f16, int batch, float* out, cudaStream_t st) {
     if (!u->finalized) { u->error = "forward before finalize"; return 1; }
+    if (check_err_flag(u)) return 1;          // an earlier (asynchronous) forward timed out: do not hand out more garbage
     if (batch < 1 || batch > u->NBmax) { u->error = "batch exceeds max_batch"; return 1; }
     // point the first convolution at the caller's grid and the head at the caller's output
     ConvOp* fc = u->first_conv;
@@ -608,7 +620,10 @@ int unet_launch_count(UNet* u) {
     return n + (int)u->ops.size();
 }
 double unet_flops(UNet* u) { return u->flops; }
-int unet_check(UNet* u) { return check_err_flag(u); }
+int unet_check(UNet* u) {
+    if (cudaDeviceSynchronize() != cudaSuccess) { u->error = "CUDA error"; return 1; }
+    return check_err_flag(u);
+}
 void unet_destroy(UNet* u) { delete u; }
 
 }  // namespace pixie

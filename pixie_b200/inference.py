@@ -53,15 +53,24 @@ class MaterialFieldPredictor:
                                                       C.c_void_p(out.data_ptr()), n, G ** 3, self.n_classes, C.c_void_p(st)))
         return out
 
+    def check(self):
+        """Raises PixieError if a convolution of either network gave up waiting on its pipeline (the flag the kernels set
+        instead of hanging). Synchronises the device."""
+        self.seg_network.check()
+        self.cont_network.check()
+
     def predict_packed_host_stream(self, feats_pinned, outs_pinned=None):
         """Many scenes end to end with HOST buffers, software-pipelined: while scene i runs through the two networks, scene i+1's
         grid (268 MB at 64^3 x 512) is already crossing PCIe on a copy stream into the other of two device buffers. Per scene the
         same work as `predict_packed_host` (H2D grid, both networks, packing, D2H field); returns the list of pinned outputs after
-        everything has finished. `feats_pinned`: sequence of pinned fp16 (N, D, H, W, C) tensors (N <= max_batch)."""
-        feats = list(feats_pinned)
+        everything has finished.
+
+        `feats_pinned`: iterable of pinned fp16 (N, D, H, W, C) tensors (N <= max_batch), or of objects with a `.tensor`
+        attribute such as `voxel_io.scene_stream` yields. It is consumed LAZILY, one scene ahead of the networks, and every item
+        that has an `h2d_done` attribute gets the CUDA event recorded after its host->device copy: a producer that recycles
+        pinned buffers (scene_stream does) waits on that event before it overwrites the buffer."""
         G = self.grid_size
-        if outs_pinned is None:
-            outs_pinned = [torch.empty((f.shape[0], 3 + self.n_classes, G, G, G), dtype=torch.float32).pin_memory() for f in feats]
+        outs = [] if outs_pinned is None else list(outs_pinned)
         with torch.cuda.device(self.device):
             if self._pipe is None:
                 nb = self.max_batch
@@ -76,23 +85,33 @@ class MaterialFieldPredictor:
             P = self._pipe
             main = torch.cuda.current_stream(self.device)
             cs = P["copy_stream"]
-            copied = [torch.cuda.Event() for _ in feats]
-            consumed = [torch.cuda.Event() for _ in feats]
+            consumed = []
             cs.wait_stream(main)
-            for i, f in enumerate(feats):
+            for i, item in enumerate(feats_pinned):
+                f = item.tensor if hasattr(item, "tensor") else item
                 n, slot = f.shape[0], i % 2
+                if n > self.max_batch:
+                    raise ValueError("batch exceeds max_batch")
+                if i >= len(outs):
+                    outs.append(torch.empty((n, 3 + self.n_classes, G, G, G), dtype=torch.float32).pin_memory())
+                copied = torch.cuda.Event()
                 with torch.cuda.stream(cs):
                     if i >= 2:
                         cs.wait_event(consumed[i - 2])          # the networks are done reading this input slot
                     P["in"][slot][:n].copy_(f, non_blocking=True)
-                    copied[i].record(cs)
-                main.wait_event(copied[i])
+                    copied.record(cs)
+                if hasattr(item, "h2d_done"):
+                    item.h2d_done = copied                      # the producer may rewrite the pinned buffer after this event
+                main.wait_event(copied)
                 seg, cont = self.predict(P["in"][slot][:n], P["seg"][slot][:n], P["cont"][slot][:n])
-                consumed[i].record(main)
+                ev = torch.cuda.Event()
+                ev.record(main)
+                consumed.append(ev)
                 self.pack(seg, cont, P["out"][slot][:n])
-                outs_pinned[i].copy_(P["out"][slot][:n], non_blocking=True)     # stream-ordered: slot reuse two scenes later is safe
+                outs[i].copy_(P["out"][slot][:n], non_blocking=True)     # stream-ordered: slot reuse two scenes later is safe
             main.synchronize()
-        return outs_pinned
+            self.check()
+        return outs
 
     def predict_packed_host(self, feat_pinned: torch.Tensor, out_pinned: Optional[torch.Tensor] = None) -> torch.Tensor:
         """End to end with HOST buffers: pinned fp16 (N, D, H, W, C) -> pinned fp32 (N, 3+n_classes, D,H,W).
@@ -109,4 +128,5 @@ class MaterialFieldPredictor:
             self.pack(seg, cont, self._packed_dev[:n])
             out_pinned.copy_(self._packed_dev[:n], non_blocking=True)
             torch.cuda.current_stream().synchronize()
+            self.check()
         return out_pinned

@@ -171,10 +171,10 @@ class MPM_Simulator_WARP:
 
     @property
     def _t(self):
-        """Particle / model tensors in the caller's order. The default native path works on them in place; the opt-in
-        tiled path keeps a sorted private copy between steps, so any access goes through a sync (results written back,
-        and — since the caller may now modify the tensors in place like the reference's zero-copy exports allow —
-        re-read at the next step). The sync is a no-op on the default path."""
+        """Particle / model tensors in the caller's order. The default native path keeps a cell-sorted private copy
+        between steps, so any access goes through a sync (results written back, and — since the caller may now modify
+        the tensors in place like the reference's zero-copy exports allow — re-read at the next step). The sync is a
+        no-op when nothing was stepped since the last access, and on the direct (slab) path."""
         if self._handle is not None:
             _lib.check(_lib.load().pixie_mpm_sync(self._handle, self._stream()))
         return self._tensors

@@ -51,15 +51,33 @@ def load_mask(path: str) -> torch.Tensor:
     return torch.from_numpy(np.load(path).astype(np.float32))
 
 
-def scene_stream(scene_dirs: Sequence[str], n_buffers: int = 3) -> Iterator[Tuple[str, torch.Tensor]]:
-    """Yields (scene_dir, pinned grid) for every scene, cycling through `n_buffers` host buffers (a buffer is rewritten only
-    `n_buffers` scenes later, after `predict_packed_host_stream` has long consumed it)."""
+class SceneGrid:
+    """One scene of `scene_stream`: `.dir`, the pinned `.tensor`, and `.h2d_done` — the CUDA event after which the pinned
+    buffer may be rewritten (set by the consumer, e.g. MaterialFieldPredictor.predict_packed_host_stream)."""
+    __slots__ = ("dir", "tensor", "h2d_done")
+
+    def __init__(self, d: str, tensor: torch.Tensor):
+        self.dir, self.tensor, self.h2d_done = d, tensor, None
+
+    def __iter__(self):              # unpacks as (scene_dir, grid)
+        return iter((self.dir, self.tensor))
+
+
+def scene_stream(scene_dirs: Sequence[str], n_buffers: int = 3) -> Iterator[SceneGrid]:
+    """Yields a SceneGrid for every scene, cycling through `n_buffers` pinned host buffers. Before a buffer is rewritten the
+    generator waits for the `h2d_done` event of the scene that used it last, so a consumer that copies asynchronously only has
+    to record that event (it must have finished with a scene's buffer by other means if it leaves `h2d_done` unset). Meant to
+    be consumed lazily — `predict_packed_host_stream(scene_stream(dirs))` — so that at most `n_buffers` scenes are in flight."""
     bufs = [None] * n_buffers
+    last = [None] * n_buffers
     for i, d in enumerate(scene_dirs):
         path = os.path.join(d, FEATURE_FILE)
         slot = i % n_buffers
+        if last[slot] is not None and last[slot].h2d_done is not None:
+            last[slot].h2d_done.synchronize()               # the device has read the previous content of this buffer
         try:
             bufs[slot] = load_feature_grid(path, out=bufs[slot])
         except ValueError:
             bufs[slot] = load_feature_grid(path)           # grid shape changed between scenes
-        yield d, bufs[slot]
+        last[slot] = SceneGrid(d, bufs[slot])
+        yield last[slot]

@@ -82,11 +82,3 @@ def test_material_name_quirk():
     assert get_material_name("jelly") == 0 and get_material_name("rigid") == 6 and get_material_name("sand") == 2
     assert get_material_name("fluid") == -1 and get_material_name(3) == -1
     assert get_material_id("snow") == 5
-
-
-def test_conv_phase_plan_host_logic(built_lib):
-    """K-phase bookkeeping of the implicit GEMM (pure host code, exercised through the bring-up binary's
-    object file is not possible without a GPU; here we only check the packed-K arithmetic used by docs)."""
-    # 3x3x3 stride-1: 3 phases (kw) per 64-channel chunk, 9 weight tiles each
-    cin, chunks = 128, 2
-    assert chunks * 3 * 9 * 64 == 27 * cin

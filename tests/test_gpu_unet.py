@@ -100,6 +100,30 @@ def test_input_layout_paths_agree(built_lib, cuda_dev):
         net.forward_host(torch.zeros(3, G, G, G, C, dtype=torch.float16))
 
 
+def test_pack_predictions_matches_reference_packing(built_lib, cuda_dev):
+    """`pixie_pack_predictions` against the reference's own statements: `th.argmax(seg_logits, dim=1)`
+    (inference_combined.py:125) and the one-hot packing of save_predictions (:173-199: continuous channels first, then
+    np.eye(n_classes)[label] moved to channel-first). Exact ties between class logits must resolve to the FIRST maximum,
+    like torch.argmax / np.argmax."""
+    from pixie_b200.inference import MaterialFieldPredictor
+    G, K = 16, 8
+    pred = MaterialFieldPredictor(feature_channels=64, grid_size=G, device="cuda:0", max_batch=2, precision="fp16x3", **O.DEFAULT_CFG)
+    g = torch.Generator().manual_seed(3)
+    seg = torch.randn(2, K, G, G, G, generator=g)
+    cont = torch.randn(2, 3, G, G, G, generator=g)
+    # ties: two, three and all classes equal to the maximum, at known voxels
+    seg[0, :, 0, 0, 0] = 1.5
+    seg[0, :, 0, 0, 1] = torch.tensor([0.1, 2.0, -1.0, 2.0, 0.3, 2.0, 0.0, 1.0])
+    seg[1, :, 3, 2, 1] = torch.tensor([-3.0, -3.0, 7.0, 0.0, 0.0, 0.0, 0.0, 7.0])
+    seg[1, :, 5, 5, 5] = float("-inf"); seg[1, 6, 5, 5, 5] = -1e30
+    out = pred.pack(seg.cuda(), cont.cuda()).cpu()
+    labels = torch.argmax(seg, dim=1)                                                      # inference_combined.py:125
+    onehot = torch.from_numpy(np.eye(K, dtype=np.float32)[labels.numpy()]).permute(0, 4, 1, 2, 3)   # :186-191
+    want = torch.cat([cont, onehot], dim=1)
+    assert torch.equal(out, want)
+    assert labels[0, 0, 0, 0] == 0 and labels[0, 0, 0, 1] == 1 and labels[1, 3, 2, 1] == 2 and labels[1, 5, 5, 5] == 6
+
+
 def test_pipelined_host_stream_equals_single_calls(built_lib, cuda_dev):
     """predict_packed_host_stream (double-buffered H2D overlapping the networks) = predict_packed_host scene by scene,
     including when the two input slots and the graph cache are cycled more than once."""
@@ -110,12 +134,47 @@ def test_pipelined_host_stream_equals_single_calls(built_lib, cuda_dev):
     pred.load_state_dicts(seg.state_dict(), reg.state_dict())
     scenes = [O.synthetic_features(1, C, G, seed=10 + i).permute(0, 2, 3, 4, 1).contiguous().to(torch.float16).pin_memory() for i in range(5)]
     single = [pred.predict_packed_host(s).clone() for s in scenes]
+    # the first scene also against the oracle networks + the reference's packing (not only against ourselves)
+    with torch.no_grad():
+        x0 = scenes[0].float().permute(0, 4, 1, 2, 3).contiguous()
+        ys, yr = seg(x0), reg(x0)
+    assert (single[0][:, :3] - yr).abs().max() < TOL["fp16x3"]
+    top2 = ys.topk(2, dim=1).values
+    confident = (top2[:, 0] - top2[:, 1]) > 10 * TOL["fp16x3"]
+    assert (single[0][:, 3:].argmax(1) == ys.argmax(1))[confident].all() and (single[0][:, 3:].sum(1) == 1).all()
     piped = pred.predict_packed_host_stream(scenes)
-    piped2 = pred.predict_packed_host_stream(scenes[::-1])
+    piped2 = pred.predict_packed_host_stream(iter(scenes[::-1]))                          # a generator: consumed lazily
     for i in range(5):
         assert (piped[i][:, :3] - single[i][:, :3]).abs().max() < 1e-4
         assert (piped[i][:, 3:] == single[i][:, 3:]).float().mean() > 0.9999          # one-hot argmax
         assert (piped2[4 - i][:, :3] - single[i][:, :3]).abs().max() < 1e-4
+
+
+def test_scene_stream_from_npy_files_through_host_pipeline(built_lib, cuda_dev, tmp_path):
+    """voxel_io.scene_stream -> predict_packed_host_stream from real clip_features_features.npy files, with MORE scenes than
+    pinned buffers: every scene's output must equal its own single-scene result (a recycled pinned buffer must not be
+    rewritten before the device has read it)."""
+    from pixie_b200 import voxel_io as V
+    from pixie_b200.inference import MaterialFieldPredictor
+    C, G, n_scenes = 64, 16, 7
+    seg, reg = O.build_pair(C, G, seed=8)
+    pred = MaterialFieldPredictor(feature_channels=C, grid_size=G, device="cuda:0", max_batch=1, precision="fp16x3", **O.DEFAULT_CFG)
+    pred.load_state_dicts(seg.state_dict(), reg.state_dict())
+    dirs, grids = [], []
+    for i in range(n_scenes):
+        a = O.synthetic_features(1, C, G, seed=40 + i)[0].permute(1, 2, 3, 0).contiguous().to(torch.float16).numpy()   # (D, D, D, C) fp16
+        d = os.path.join(str(tmp_path), f"obj{i}")
+        os.makedirs(d)
+        np.save(os.path.join(d, V.FEATURE_FILE), a)
+        dirs.append(d); grids.append(a)
+    single = [pred.predict_packed_host(torch.from_numpy(a)[None].pin_memory()).clone() for a in grids]
+    outs = pred.predict_packed_host_stream(V.scene_stream(dirs, n_buffers=2))
+    assert len(outs) == n_scenes
+    for i in range(n_scenes):
+        assert (outs[i][:, :3] - single[i][:, :3]).abs().max() < 1e-4, i
+        assert (outs[i][:, 3:] == single[i][:, 3:]).float().mean() > 0.9999, i
+    # distinct scenes really give distinct fields (the test would pass trivially otherwise)
+    assert (single[0][:, :3] - single[1][:, :3]).abs().max() > 1e-2
 
 
 @pytest.mark.parametrize("C", [3, 32])
@@ -142,11 +201,11 @@ def test_missing_weights_fail_loudly(built_lib, cuda_dev):
 
 
 def test_full_size_64_cubed_512(built_lib, cuda_dev):
-    """BASELINE config 2 size. The oracle forward takes several seconds on the host; checked once for the
-    regression network, plus size-independent properties: determinism to round-off (split-K uses float
-    atomics at the coarse levels) and batch/single consistency through the staging path."""
+    """BASELINE config 2 size. The oracle forward takes several seconds on the host; checked for both networks (the
+    segmentation one in the default precision), plus size-independent properties: determinism to round-off (split-K
+    uses float atomics at the coarse levels) and batch/single consistency through the staging path."""
     C, G = 512, 64
-    _, reg = O.build_pair(C, G, seed=0)
+    seg, reg = O.build_pair(C, G, seed=0)
     x16 = (torch.randn(1, G, G, G, C, generator=torch.Generator().manual_seed(1)) * 0.05).to(torch.float16)
     with torch.no_grad():
         y_ref = reg(x16.float().permute(0, 4, 1, 2, 3).contiguous())
@@ -159,3 +218,12 @@ def test_full_size_64_cubed_512(built_lib, cuda_dev):
         assert (y.cpu() - y_ref).abs().max() < TOL[precision]
         del net
         torch.cuda.empty_cache()
+    with torch.no_grad():
+        ys = seg(x16.float().permute(0, 4, 1, 2, 3).contiguous())
+    net = _mine("SegmentationUNet", C, G, 8, "fp16x3", seg.state_dict(), max_batch=1)
+    zs = net.forward_channels_last_f16(x16.cuda()).cpu()
+    net.check()
+    assert (zs - ys).abs().max() < TOL["fp16x3"]
+    top2 = ys.topk(2, dim=1).values
+    confident = (top2[:, 0] - top2[:, 1]) > 10 * TOL["fp16x3"]
+    assert (zs.argmax(1) == ys.argmax(1))[confident].all()

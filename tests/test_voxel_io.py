@@ -48,3 +48,27 @@ def test_scene_stream_cycles_buffers(tmp_path, monkeypatch):
         seen.append((d, float(t[0, 0, 0, 0, 0]), t.data_ptr()))
     assert [s[1] for s in seen] == [0.0, 1.0, 2.0, 3.0, 4.0]
     assert seen[0][2] == seen[2][2] == seen[4][2] and seen[1][2] == seen[3][2] and seen[0][2] != seen[1][2]
+
+
+def test_scene_stream_waits_for_the_consumer_before_rewriting(tmp_path, monkeypatch):
+    """A recycled pinned buffer is rewritten only after the `h2d_done` event its last user recorded (the consumer's
+    host->device copy is asynchronous)."""
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: False)
+
+    class Ev:
+        def __init__(self):
+            self.waited = False
+
+        def synchronize(self):
+            self.waited = True
+
+    dirs = [_write(str(tmp_path), f"o{i}", np.full((4, 4, 4, 8), i, np.float16)) for i in range(5)]
+    items = []
+    for item in V.scene_stream(dirs, n_buffers=2):
+        # by the time scene i is produced, the generator must have waited for scene i-2 (same buffer)
+        if len(items) >= 2:
+            assert items[-2].h2d_done.waited
+            assert not items[-1].h2d_done.waited
+        item.h2d_done = Ev()
+        items.append(item)
+    assert [float(it.tensor[0, 0, 0, 0, 0]) for it in items[-2:]] == [3.0, 4.0]
