@@ -44,8 +44,10 @@ typedef struct {
     int grid_size;            /* D = H = W of the voxel grid (64)                                     */
     int out_channels;         /* 8 (num_classes, segmentation) or 3 (regression)                      */
     int max_batch;            /* largest batch forward() will be called with                          */
-    int precision;            /* 0: fp16 operands, fp32 accumulate (1 tensor-core pass)
-                                 1: split fp16 hi/lo operands (3 passes, ~fp32 products)             */
+    int precision;            /* 0: fp16 operands, fp32 accumulate (1 tensor-core pass; max-abs ~5e-3 vs fp32)
+                               * 1: "fp16x3": operands split in fp16 hi + lo, three fp16 passes (max-abs ~6e-5)
+                               * 2: "fp16e5": one fp16 pass + one E5M2 pass (kind::f8f6f4, twice the MMA rate) that adds
+                               *    a_lo*w + a*w_lo = 2 pass-equivalents (max-abs ~3e-4, inside the 1e-3 tolerance) */
 } pixie_unet_config;
 
 /* Constructor arguments of SegmentationUNet / RegressionUNet (attention_resolutions must be ()). */
@@ -218,10 +220,11 @@ int pixie_mpm_apply_additional_params(pixie_mpm_t h, const float* boxes, int n_b
 int pixie_mpm_select_box(pixie_mpm_t h, const float point[3], const float size[3], int* mask_dev, void* stream);
 int pixie_mpm_select_cylinder(pixie_mpm_t h, const float point[3], const float normal[3],
                               float half_height, float radius, int* mask_dev, void* stream);
-/* The default path works in place on the bound arrays (pixie_mpm_sync is then a no-op). The opt-in tiled path
- * (PIXIE_MPM_TILED=1) keeps a tile-sorted private copy of the particle state between steps: pixie_mpm_sync writes the
- * results back into the bound arrays and must precede any read of them; every other entry point that touches the bound
- * arrays calls it internally. After a sync the caller may modify its arrays: the next step re-reads them. */
+/* The default path keeps a cell-sorted struct-of-arrays private copy of the particle state between steps (the bound
+ * arrays stay in the caller's order and are what every other entry point reads): pixie_mpm_sync writes the results back
+ * into the bound arrays and must precede any read of them; every other entry point that touches the bound arrays calls it
+ * internally. After a sync the caller may modify its arrays: the next step re-reads them. It is a no-op when nothing was
+ * stepped since the last sync and on the direct path (slab-decomposed runs, PIXIE_MPM_DIRECT=1), which works in place. */
 int pixie_mpm_sync(pixie_mpm_t h, void* stream);
 /* ---- Spatially sharded rollout (BASELINE config 5: one large scene, slab decomposition along x; no reference
  * counterpart — the reference hard-wires "cuda:0", gs_simulation.py:441). One handle per rank holds the particles whose
@@ -237,7 +240,25 @@ int pixie_mpm_substep_finish(pixie_mpm_t h, double dt, void* stream);    /* grid
 /* Borrowed pointers to the grid arrays owned by the handle: grid_m [n^3], grid_v_in / grid_v_out
  * [n^3][3] as left by the last substep (for tests). */
 int pixie_mpm_grid_ptrs(pixie_mpm_t h, float** grid_mv4, float** grid_v_out);
-int pixie_mpm_launches_per_substep(pixie_mpm_t h);
+/* ---- Slab mode of the default path (BASELINE config 5, no reference counterpart). Every handle owns an exchange buffer
+ * [256-byte flag block][{mv.xyz, m} grid, float4[n_grid^3], x slowest]; pixie_mpm_slab_attach gives it the x-neighbours'
+ * buffers (pointers valid in this process: from pixie_ipc_open for a neighbour in another process, or the neighbour's own
+ * pointer inside one process). A substep is then three device phases with flag handshakes between neighbours and no host
+ * round trip: scatter (particle kernel; stencils may reach `slack` + 2 planes into the neighbours' ranges), halo (overlap
+ * totals = own + neighbour partial sums, read over NVLink), finish (grid update on owned + overlap planes, clear).
+ * pixie_mpm_step runs whole substeps (CUDA graph); pixie_mpm_slab_phase runs ONE phase (0 scatter, 1 halo, 2 finish) so
+ * that a single-process driver can sequence the phases of several slabs on one stream. Particles whose stencil base
+ * leaves [x0 - slack, x1 + slack) raise error 2 (migrate more often); a neighbour that never shows up raises error 1. */
+int pixie_mpm_exchange_buffer(pixie_mpm_t h, void** base, size_t* bytes);
+int pixie_mpm_slab_attach(pixie_mpm_t h, int x0, int x1, int slack, const void* left_xbuf, const void* right_xbuf);
+int pixie_mpm_slab_phase(pixie_mpm_t h, int phase, double dt, void* stream);
+int pixie_mpm_slab_error(pixie_mpm_t h, int* flag);
+/* cudaIpc plumbing for the exchange buffers (64-byte opaque handles, exchanged by the caller, e.g. over torch.distributed). */
+int pixie_ipc_export(const void* dev_ptr, unsigned char handle[64]);
+int pixie_ipc_open(const unsigned char handle[64], void** dev_ptr);
+int pixie_ipc_close(void* dev_ptr);
+/* Kernels of this library launched for the handle so far (CUDA-graph replays count their nodes; cub's sort passes do not count). */
+long long pixie_mpm_launch_count(pixie_mpm_t h);
 void pixie_mpm_destroy(pixie_mpm_t h);
 
 #ifdef __cplusplus

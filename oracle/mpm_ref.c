@@ -724,6 +724,13 @@ void mpmref_planes_add(sim_t* s, int a, int b, const double* in) {
         s->grid_m[i] += (real)in[4 * k + 3];
     }
 }
+void mpmref_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
 int mpmref_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -57,6 +57,7 @@ def _lib(precision: str) -> C.CDLL:
     lib.mpmref_stress_of_F.argtypes = [C.c_void_p, C.c_int]
     lib.mpmref_step.argtypes = [C.c_void_p, C.c_int, C.c_double]
     lib.mpmref_num_threads.restype = C.c_int
+    lib.mpmref_set_num_threads.argtypes = [C.c_int]
     lib.mpmref_set_active.argtypes = [C.c_void_p, C.c_int]
     lib.mpmref_scatter.argtypes = [C.c_void_p, C.c_double]
     lib.mpmref_finish.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_int]
@@ -216,6 +217,10 @@ class MpmRef:
 
     def num_threads(self) -> int:
         return int(self.lib.mpmref_num_threads())
+
+    def set_num_threads(self, n: int):
+        """OpenMP threads of the oracle (torchrun exports OMP_NUM_THREADS=1, which would starve a CPU baseline)."""
+        self.lib.mpmref_set_num_threads(int(n))
 
 
 # Synthetic scene of BASELINE config 3: shared with bench.py, lives with the other synthetic-data

@@ -97,7 +97,14 @@ _SIGNATURES = {
     "pixie_mpm_substep_scatter": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p]),
     "pixie_mpm_substep_finish": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p]),
     "pixie_mpm_grid_ptrs": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
-    "pixie_mpm_launches_per_substep": (C.c_int, [C.c_void_p]),
+    "pixie_mpm_launch_count": (C.c_longlong, [C.c_void_p]),
+    "pixie_mpm_exchange_buffer": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
+    "pixie_mpm_slab_attach": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "pixie_mpm_slab_phase": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_void_p]),
+    "pixie_mpm_slab_error": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
+    "pixie_ipc_export": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "pixie_ipc_open": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "pixie_ipc_close": (C.c_int, [C.c_void_p]),
     "pixie_mpm_destroy": (None, [C.c_void_p]),
 }
 

@@ -176,7 +176,28 @@ int pixie_mpm_set_active_count(pixie_mpm_t h, int n_active) { MPM_CALL(pixie::mp
 int pixie_mpm_substep_scatter(pixie_mpm_t h, double dt, void* s) { MPM_CALL(pixie::mpm_substep_scatter(h->m, dt, (cudaStream_t)s)); }
 int pixie_mpm_substep_finish(pixie_mpm_t h, double dt, void* s) { MPM_CALL(pixie::mpm_substep_finish(h->m, dt, (cudaStream_t)s)); }
 int pixie_mpm_grid_ptrs(pixie_mpm_t h, float** mv4, float** v4) { MPM_CALL(pixie::mpm_grid_ptrs(h->m, mv4, v4)); }
-int pixie_mpm_launches_per_substep(pixie_mpm_t h) { (void)h; return 3; }
+int pixie_mpm_exchange_buffer(pixie_mpm_t h, void** base, size_t* bytes) { MPM_CALL(pixie::mpm_exchange_buffer(h->m, base, bytes)); }
+int pixie_mpm_slab_attach(pixie_mpm_t h, int x0, int x1, int slack, const void* left, const void* right) {
+    MPM_CALL(pixie::mpm_slab_attach(h->m, x0, x1, slack, left, right));
+}
+int pixie_mpm_slab_phase(pixie_mpm_t h, int phase, double dt, void* s) { MPM_CALL(pixie::mpm_slab_phase(h->m, phase, dt, (cudaStream_t)s)); }
+int pixie_mpm_slab_error(pixie_mpm_t h, int* flag) { MPM_CALL(pixie::mpm_slab_error(h->m, flag)); }
+int pixie_ipc_export(const void* dev_ptr, unsigned char handle[64]) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t size");
+    cudaIpcMemHandle_t hd;
+    if (cudaIpcGetMemHandle(&hd, const_cast<void*>(dev_ptr)) != cudaSuccess) return set_err(std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(cudaGetLastError()));
+    memcpy(handle, &hd, 64);
+    return 0;
+}
+int pixie_ipc_open(const unsigned char handle[64], void** dev_ptr) {
+    cudaIpcMemHandle_t hd;
+    memcpy(&hd, handle, 64);
+    if (cudaIpcOpenMemHandle(dev_ptr, hd, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess)
+        return set_err(std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(cudaGetLastError()));
+    return 0;
+}
+int pixie_ipc_close(void* dev_ptr) { return cudaIpcCloseMemHandle(dev_ptr) == cudaSuccess ? 0 : set_err("cudaIpcCloseMemHandle failed"); }
+long long pixie_mpm_launch_count(pixie_mpm_t h) { return h ? pixie::mpm_launch_count(h->m) : 0; }
 void pixie_mpm_destroy(pixie_mpm_t h) {
     if (!h) return;
     pixie::mpm_destroy(h->m);

@@ -6,6 +6,8 @@
 #include <cstdio>
 #include <cstring>
 
+#include <cuda_fp8.h>
+
 namespace pixie {
 
 using namespace ptx;
@@ -103,21 +105,27 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvKernelParams& p, int 
 // accumulators starting at acc0. Everything that depends on (kh, k4) is a compile-time immediate so the single issuing
 // thread spends ~4 instructions per tcgen05.mma; with run-time strides it spends ~20 and becomes the kernel's bottleneck
 // (r01: 240 instructions per slab at ~7 cycles each vs 12 x 96 tensor-pipe cycles).
-template <int BN, int TWv>
+template <bool F8, bool ACC>
+__device__ __forceinline__ void umma_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc) {
+    if (F8) umma_f8_lohi<ACC>(d_tmem, a_lo, b_lo, hi, idesc);
+    else umma_f16_lohi<ACC>(d_tmem, a_lo, b_lo, hi, idesc);
+}
+// (F8: the same smem geometry — 128-byte rows, four 32-byte K steps — read as E5M2 with K = 32 per instruction.)
+template <int BN, int TWv, bool F8>
 __device__ __forceinline__ void issue_slab_3x3(uint32_t acc0, uint32_t a_lo0, uint32_t b_lo0, uint32_t hi, uint32_t idA,
                                                uint32_t id_old, uint32_t id1, int nold, bool fresh) {
     constexpr uint32_t kKh = (uint32_t)(TWv * 128) >> 4, kTap = (uint32_t)(BN * 128) >> 4;
     if (fresh) {
         // the newest plane's accumulator is overwritten by its first MMA, the older planes accumulate
-        if (nold > 0) umma_f16_lohi<true>(acc0, a_lo0, b_lo0, hi, id_old);
-        umma_f16_lohi<false>(acc0 + (uint32_t)(nold * BN), a_lo0, b_lo0 + (uint32_t)nold * kTap, hi, id1);
+        if (nold > 0) umma_lohi<F8, true>(acc0, a_lo0, b_lo0, hi, id_old);
+        umma_lohi<F8, false>(acc0 + (uint32_t)(nold * BN), a_lo0, b_lo0 + (uint32_t)nold * kTap, hi, id1);
     } else {
-        umma_f16_lohi<true>(acc0, a_lo0, b_lo0, hi, idA);
+        umma_lohi<F8, true>(acc0, a_lo0, b_lo0, hi, idA);
     }
 #pragma unroll
     for (int i = 1; i < 12; ++i) {
         const uint32_t kh = (uint32_t)(i >> 2), k4 = (uint32_t)(i & 3);
-        umma_f16_lohi<true>(acc0, a_lo0 + kh * kKh + 2u * k4, b_lo0 + kh * 3u * kTap + 2u * k4, hi, idA);
+        umma_lohi<F8, true>(acc0, a_lo0 + kh * kKh + 2u * k4, b_lo0 + kh * 3u * kTap + 2u * k4, hi, idA);
     }
 }
 
@@ -212,8 +220,10 @@ conv3d_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
         // 23 % busy, issue thread never waiting).
         int ws = 0, wph = 0, ss = 0, sph = 0, as = 0, aph = 0;
         const int max_blk = min(3, 256 / p.block_n);                             // accumulator blocks one MMA may span
-        const uint32_t idesc1 = make_idesc_f16(128, (uint32_t)p.block_n), idesc2 = make_idesc_f16(128, (uint32_t)(2 * p.block_n)),
-                       idesc3 = make_idesc_f16(128, (uint32_t)(3 * p.block_n));
+        const uint32_t idesc1_h = make_idesc_f16(128, (uint32_t)p.block_n), idesc2_h = make_idesc_f16(128, (uint32_t)(2 * p.block_n)),
+                       idesc3_h = make_idesc_f16(128, (uint32_t)(3 * p.block_n));
+        const uint32_t idesc1_q = make_idesc_e5m2(128, (uint32_t)p.block_n), idesc2_q = make_idesc_e5m2(128, (uint32_t)(2 * p.block_n)),
+                       idesc3_q = make_idesc_e5m2(128, (uint32_t)(3 * p.block_n));
         const uint64_t desc_fixed = (make_sw128_desc(0, 1024) ^ p.desc_xor);   // everything but the start address
         const uint32_t desc_lo = (uint32_t)desc_fixed, desc_hi = (uint32_t)(desc_fixed >> 32);
         const bool fast3 = (p.block_n == 64 || p.block_n == 128) && (p.TW == 16 || p.TW == 8);
@@ -229,6 +239,8 @@ conv3d_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
             for (int ph = t.ph_begin; ph < t.ph_end && ok; ++ph) {
                 const ConvPhase P = p.phases[ph];
                 const int n_kd = P.n_kd, n_kh = P.n_kh;
+                const bool f8 = P.f8 != 0;                       // warp-uniform
+                const uint32_t idesc1 = f8 ? idesc1_q : idesc1_h, idesc2 = f8 ? idesc2_q : idesc2_h, idesc3 = f8 ? idesc3_q : idesc3_h;
                 ok = mbar_wait(&ctl->wfull[ws], wph, abort_flag);
                 if (!ok) break;
                 const uint32_t w16 = (w_base0 + (uint32_t)(ws * p.w_stage_bytes)) >> 4;
@@ -255,12 +267,20 @@ conv3d_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
                             const uint32_t id_old = nold == 1 ? idesc1 : idesc2;
                             const uint32_t a_lo0 = desc_lo | (s16 & 0x3FFFu);
                             const uint32_t b_lo0 = desc_lo | ((w16 + wblk0 * tap_stride16) & 0x3FFFu);
-                            if (p.block_n == 64) {
-                                if (p.TW == 16) issue_slab_3x3<64, 16>(acc0, a_lo0, b_lo0, desc_hi, idA, id_old, idesc1, nold, fresh);
-                                else issue_slab_3x3<64, 8>(acc0, a_lo0, b_lo0, desc_hi, idA, id_old, idesc1, nold, fresh);
+                            if (f8) {
+                                if (p.block_n == 64) {
+                                    if (p.TW == 16) issue_slab_3x3<64, 16, true>(acc0, a_lo0, b_lo0, desc_hi, idA, id_old, idesc1, nold, fresh);
+                                    else issue_slab_3x3<64, 8, true>(acc0, a_lo0, b_lo0, desc_hi, idA, id_old, idesc1, nold, fresh);
+                                } else {
+                                    if (p.TW == 16) issue_slab_3x3<128, 16, true>(acc0, a_lo0, b_lo0, desc_hi, idA, id_old, idesc1, nold, fresh);
+                                    else issue_slab_3x3<128, 8, true>(acc0, a_lo0, b_lo0, desc_hi, idA, id_old, idesc1, nold, fresh);
+                                }
+                            } else if (p.block_n == 64) {
+                                if (p.TW == 16) issue_slab_3x3<64, 16, false>(acc0, a_lo0, b_lo0, desc_hi, idA, id_old, idesc1, nold, fresh);
+                                else issue_slab_3x3<64, 8, false>(acc0, a_lo0, b_lo0, desc_hi, idA, id_old, idesc1, nold, fresh);
                             } else {
-                                if (p.TW == 16) issue_slab_3x3<128, 16>(acc0, a_lo0, b_lo0, desc_hi, idA, id_old, idesc1, nold, fresh);
-                                else issue_slab_3x3<128, 8>(acc0, a_lo0, b_lo0, desc_hi, idA, id_old, idesc1, nold, fresh);
+                                if (p.TW == 16) issue_slab_3x3<128, 16, false>(acc0, a_lo0, b_lo0, desc_hi, idA, id_old, idesc1, nold, fresh);
+                                else issue_slab_3x3<128, 8, false>(acc0, a_lo0, b_lo0, desc_hi, idA, id_old, idesc1, nold, fresh);
                             }
                         } else
                         for (int kh = 0; kh < n_kh; ++kh) {
@@ -275,11 +295,13 @@ conv3d_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
                                     const int cnt = min(max_blk, nold - b);
                                     const uint32_t idn = (cnt == 1) ? idesc1 : (cnt == 2 ? idesc2 : idesc3);
                                     const uint64_t db = desc_fixed | (uint64_t)((b16 + (uint32_t)b * tap_stride16 + 2u * k4) & 0x3FFFu);
-                                    umma_f16(acc0 + (uint32_t)(b * p.block_n), da, db, idn, 1u);
+                                    if (f8) umma_f8(acc0 + (uint32_t)(b * p.block_n), da, db, idn, 1u);
+                                    else umma_f16(acc0 + (uint32_t)(b * p.block_n), da, db, idn, 1u);
                                 }
                                 if (split_new) {
                                     const uint64_t db = desc_fixed | (uint64_t)((b16 + (uint32_t)(nblk - 1) * tap_stride16 + 2u * k4) & 0x3FFFu);
-                                    umma_f16(acc0 + (uint32_t)((nblk - 1) * p.block_n), da, db, idesc1, 0u);
+                                    if (f8) umma_f8(acc0 + (uint32_t)((nblk - 1) * p.block_n), da, db, idesc1, 0u);
+                                    else umma_f16(acc0 + (uint32_t)((nblk - 1) * p.block_n), da, db, idesc1, 0u);
                                 }
                             }
                         }
@@ -620,7 +642,7 @@ std::vector<ConvPhase> conv_build_phases(const ConvDesc& d) {
                 ConvPhase P{};
                 P.src = (int8_t)conv_slot_of(slots, s.src, 1);
                 P.dw = 0; P.dh0 = 0; P.dd0 = 0; P.n_kh = 1; P.n_kd = 1;
-                P.c0 = (int16_t)(c * 64); P.wtile_base = wtile; wtile += 1;
+                P.c0 = (int16_t)(c * 64); P.wtile_base = wtile; wtile += 1; P.f8 = s.f8;
                 ph.push_back(P);
             }
         } else if (d.stride == 1) {
@@ -629,7 +651,7 @@ std::vector<ConvPhase> conv_build_phases(const ConvDesc& d) {
                     ConvPhase P{};
                     P.src = (int8_t)conv_slot_of(slots, s.src, 3);
                     P.dw = (int8_t)(kw - 1); P.dh0 = -1; P.dd0 = -1; P.n_kh = 3; P.n_kd = 3;
-                    P.c0 = (int16_t)(c * 64); P.wtile_base = wtile; wtile += 9;
+                    P.c0 = (int16_t)(c * 64); P.wtile_base = wtile; wtile += 9; P.f8 = s.f8;
                     ph.push_back(P);
                 }
         } else {
@@ -641,7 +663,7 @@ std::vector<ConvPhase> conv_build_phases(const ConvDesc& d) {
                             P.src = (int8_t)conv_slot_of(slots, s.src, 1);
                             P.dw = (int8_t)(kw - 1); P.dh0 = (int8_t)(kh - 1); P.dd0 = (int8_t)(kd - 1);
                             P.n_kh = 1; P.n_kd = 1;
-                            P.c0 = (int16_t)(c * 64); P.wtile_base = wtile; wtile += 1;
+                            P.c0 = (int16_t)(c * 64); P.wtile_base = wtile; wtile += 1; P.f8 = s.f8;
                             ph.push_back(P);
                         }
         }
@@ -661,15 +683,25 @@ void conv_pack_weights(const ConvDesc& d, const std::vector<const float*>& seg_w
         const int cin = seg_cin_real[si];
         const int ks = s.ks, kv = ks * ks * ks;
         const float* w = seg_weights[si];   // [Cout][cin][kd][kh][kw]
+        const float up = (float)(1 << kF8Shift), down = 1.0f / up;
+        auto e5m2 = [](float v) { return (uint8_t)__nv_cvt_float_to_fp8(v, __NV_SATFINITE, __NV_E5M2); };
         auto put = [&](int tile, int c, int kd, int kh, int kw) {
-            for (int co = 0; co < d.Cout; ++co)
+            for (int co = 0; co < d.Cout; ++co) {
+                // an f8 tile is 128 bytes per row: [e5m2(w / 2^s) x 64 | e5m2((w - fp16(w)) * 2^s) x 64]
+                uint8_t* row8 = reinterpret_cast<uint8_t*>(&packed[(size_t)co * K + (size_t)tile * 64]);
                 for (int cil = 0; cil < 64; ++cil) {
                     const int ci = c * 64 + cil;
                     if (ci >= cin) continue;
                     float v = w[((size_t)co * cin + ci) * kv + (kd * ks + kh) * ks + kw];
+                    if (s.f8) {
+                        row8[cil] = e5m2(v * down);
+                        row8[64 + cil] = e5m2((v - __half2float(__float2half(v))) * up);
+                        continue;
+                    }
                     if (s.wlo) v = v - __half2float(__float2half(v));
                     packed[(size_t)co * K + (size_t)tile * 64 + cil] = __float2half(v);
                 }
+            }
         };
         if (ks == 1) {
             for (int c = 0; c < chunks; ++c) put(wtile++, c, 0, 0, 0);

@@ -30,6 +30,7 @@
 namespace pixie {
 
 constexpr int kConvMaxSrc = 8;
+constexpr int kF8Shift = 6;        // power-of-two rebalancing between the E5M2 operands (see ConvDesc::Seg)
 constexpr int kConvThreads = 192;  // warp0 TMA, warp1 MMA, warps2-5 epilogue
 
 struct ConvPhase {        // 16 bytes, lives in global memory
@@ -41,7 +42,7 @@ struct ConvPhase {        // 16 bytes, lives in global memory
     int8_t n_kd;          // 1 or 3: kd taps served by plane marching
     int16_t c0;           // first channel of the 64-channel chunk inside the source
     int32_t wtile_base;   // index of this phase's first weight tile (64 K-columns each)
-    int32_t pad_;
+    int32_t f8;           // 1: operands are E5M2 bytes (128 per row instead of 64 halfs), issued as kind::f8f6f4
 };
 static_assert(sizeof(ConvPhase) == 16, "ConvPhase layout");
 
@@ -99,7 +100,11 @@ struct ConvDesc {
     int Cout = 0;
     // K segments: each segment is (source, kernel size 1 or 3) over all of the source's channels.
     // wlo = 1 packs the fp16 rounding residual of the weights (w - fp16(w)) for split-precision mode.
-    struct Seg { int src; int ks; int wlo = 0; };
+    // f8 = 1: an E5M2 correction segment (tensor-core rate 2x fp16). Its source rows hold, per 64-channel chunk, 64 bytes
+    // e5m2(a_lo * 2^kF8Shift) followed by 64 bytes e5m2(a * 2^-kF8Shift); its weight rows hold e5m2(w * 2^-kF8Shift) followed by
+    // e5m2(w_lo * 2^kF8Shift), so one K = 128-byte chunk accumulates a_lo*w + a*w_lo — the two first-order terms a single
+    // fp16 pass loses — into the same fp32 accumulator (`C` of such a source counts 2-byte units like the fp16 ones).
+    struct Seg { int src; int ks; int wlo = 0; int f8 = 0; };
     std::vector<ConvSrc> srcs;
     std::vector<Seg> segs;
     const __half* weights = nullptr;   // packed by pack_conv_weights(), [Cout_pad][K_total]

@@ -4,6 +4,8 @@
 //   env:   PIXIE_DESC_XOR=<hex>   xor into the high word of every smem descriptor (bring-up only)
 #include "conv3d_igemm.cuh"
 
+#include <cuda_fp8.h>
+
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -26,6 +28,7 @@ struct Case {
     bool bias, residual, planar;
     int split_k, block_n, td;
     bool timing;
+    bool f8corr = false;   // fp16 pass + E5M2 correction segment (a_lo*w + a*w_lo) on non-fp16-representable operands
 };
 
 static float frand(std::mt19937& g) { return std::uniform_real_distribution<float>(-1.f, 1.f)(g); }
@@ -49,6 +52,13 @@ int main(int argc, char** argv) {
         {"head_64_3_planar_d16", 1, 16, 1, {64}, {64}, {{0, 3}}, 3, true, false, true, 1, 0, 0, false},
         {"qkv_256_768_d8", 1, 8, 1, {256}, {256}, {{0, 1}}, 768, true, false, false, 1, 0, 0, false},
         {"conv3_256_256_d4", 1, 4, 1, {256}, {256}, {{0, 3}}, 256, true, false, false, 0, 0, 0, false},
+        {"x2_gemm1x1_128_64_d16", 1, 16, 1, {128}, {128}, {{0, 1}}, 64, true, false, false, 1, 0, 0, false, true},
+        {"x2_conv3_64_64_d16", 1, 16, 1, {64}, {64}, {{0, 3}}, 64, true, true, false, 1, 0, 0, false, true},
+        {"x2_conv3_128_128_d16", 2, 16, 1, {128}, {128}, {{0, 3}}, 128, true, false, false, 1, 0, 0, false, true},
+        {"x2_conv3_s2_64_64_d16to8", 1, 8, 2, {64}, {64}, {{0, 3}}, 64, true, false, false, 1, 0, 0, false, true},
+        {"x2_conv3_256_256_d8_splitk", 1, 8, 1, {256}, {256}, {{0, 3}}, 256, true, false, false, 0, 0, 0, false, true},
+        {"T_x2_conv3_64_64_d64", 1, 64, 1, {64}, {64}, {{0, 3}}, 64, true, false, false, 1, 0, 0, true, true},
+        {"T_x2_conv3_128_64_d64", 1, 64, 1, {128}, {128}, {{0, 3}}, 64, true, true, false, 1, 0, 0, true, true},
         {"T_conv3_64_64_d64", 1, 64, 1, {64}, {64}, {{0, 3}}, 64, true, false, false, 1, 0, 0, true},
         {"T_conv3_64_64_d64_td2", 1, 64, 1, {64}, {64}, {{0, 3}}, 64, true, false, false, 1, 0, 2, true},
         {"T_conv3_128_64_d64", 1, 64, 1, {128}, {128}, {{0, 3}}, 64, true, true, false, 1, 0, 0, true},
@@ -76,17 +86,40 @@ int main(int argc, char** argv) {
         d.Cout_pad = (c.Cout + 15) / 16 * 16;
         d.split_k = c.split_k; d.block_n = c.block_n; d.td = c.td; d.out_planar = c.planar;
 
+        const float f8up = (float)(1 << kF8Shift), f8down = 1.0f / f8up;
+        auto e5m2 = [](float v) { return (uint8_t)__nv_cvt_float_to_fp8(v, __NV_SATFINITE, __NV_E5M2); };
+        auto e5m2f = [](uint8_t b) { return __half2float(__half(__nv_cvt_fp8_to_halfraw(b, __NV_E5M2))); };
         std::vector<std::vector<__half>> h_src(c.srcC.size());
+        std::vector<std::vector<float>> h_true(c.srcC.size());          // f8corr: the un-rounded activations
+        std::vector<std::vector<uint8_t>> h_pair(c.srcC.size());        // f8corr: [e5m2(a_lo * 2^s) x 64 | e5m2(a / 2^s) x 64] per chunk
         std::vector<__half*> d_src(c.srcC.size());
+        std::vector<__half*> d_pair(c.srcC.size(), nullptr);
         for (size_t s = 0; s < c.srcC.size(); ++s) {
-            h_src[s].resize(vox_in * c.srcC[s]);
+            const int C = c.srcC[s];
+            h_src[s].resize(vox_in * C);
+            if (c.f8corr) { h_true[s].resize(vox_in * C); h_pair[s].assign(vox_in * C * 2, 0); }
             for (size_t v = 0; v < vox_in; ++v)
-                for (int ch = 0; ch < c.srcC[s]; ++ch)
-                    h_src[s][v * c.srcC[s] + ch] = __float2half(ch < c.srcCreal[s] ? frand(gen) : 0.f);
+                for (int ch = 0; ch < C; ++ch) {
+                    const float a = ch < c.srcCreal[s] ? frand(gen) : 0.f;
+                    const __half hi = __float2half(a);
+                    h_src[s][v * C + ch] = hi;
+                    if (c.f8corr) {
+                        h_true[s][v * C + ch] = a;
+                        uint8_t* row = &h_pair[s][(v * C + (size_t)(ch & ~63)) * 2];
+                        row[ch & 63] = e5m2((a - __half2float(hi)) * f8up);
+                        row[64 + (ch & 63)] = e5m2(a * f8down);
+                    }
+                }
             CK(cudaMalloc(&d_src[s], h_src[s].size() * 2));
             CK(cudaMemcpy(d_src[s], h_src[s].data(), h_src[s].size() * 2, cudaMemcpyHostToDevice));
-            d.srcs.push_back({d_src[s], c.srcC[s], Di, Di, Di});
+            d.srcs.push_back({d_src[s], C, Di, Di, Di});
         }
+        if (c.f8corr)
+            for (size_t s = 0; s < c.srcC.size(); ++s) {
+                CK(cudaMalloc(&d_pair[s], h_pair[s].size()));
+                CK(cudaMemcpy(d_pair[s], h_pair[s].data(), h_pair[s].size(), cudaMemcpyHostToDevice));
+                d.srcs.push_back({d_pair[s], c.srcC[s], Di, Di, Di});          // source index = s + n_src
+            }
         std::vector<std::vector<float>> h_w(c.segs.size());
         std::vector<const float*> wptr;
         std::vector<int> cin_real;
@@ -96,9 +129,15 @@ int main(int argc, char** argv) {
             const int cin = c.srcCreal[src];
             h_w[g].resize((size_t)c.Cout * cin * ks * ks * ks);
             const float sc = 1.0f / std::sqrt((float)cin * ks * ks * ks);
-            for (auto& x : h_w[g]) x = __half2float(__float2half(frand(gen) * sc));
+            for (auto& x : h_w[g]) x = c.f8corr ? frand(gen) * sc : __half2float(__float2half(frand(gen) * sc));
             wptr.push_back(h_w[g].data());
             cin_real.push_back(cin);
+            if (c.f8corr) {
+                ConvDesc::Seg q{src + (int)c.srcC.size(), ks, 0, 1};
+                d.segs.push_back(q);
+                wptr.push_back(h_w[g].data());
+                cin_real.push_back(cin);
+            }
         }
         std::vector<__half> packed;
         conv_pack_weights(d, wptr, cin_real, packed);
@@ -196,7 +235,7 @@ int main(int argc, char** argv) {
         std::vector<float> h_out(out_elems);
         CK(cudaMemcpy(h_out.data(), d_out, out_elems * 4, cudaMemcpyDeviceToHost));
         const size_t nsample = c.timing ? 600 : vox_out;
-        double max_err = 0, max_ref = 0;
+        double max_err = 0, max_ref = 0, max_true_err = 0, max_fp16_err = 0;
         size_t bad = 0, nan_cnt = 0;
         std::mt19937 g2(99);
         for (size_t si = 0; si < nsample; ++si) {
@@ -208,7 +247,7 @@ int main(int argc, char** argv) {
             const int od = t % Do; t /= Do;
             const int nb = (int)t;
             for (int co = 0; co < c.Cout; ++co) {
-                double acc = c.bias ? h_bias[co] : 0.0;
+                double acc = c.bias ? h_bias[co] : 0.0, acc_true = acc, acc_h = acc;
                 for (size_t g = 0; g < c.segs.size(); ++g) {
                     const int src = c.segs[g].first, ks = c.segs[g].second, pad = ks / 2;
                     const int cin = c.srcCreal[src], C = c.srcC[src];
@@ -220,8 +259,23 @@ int main(int argc, char** argv) {
                                 if (id < 0 || ih < 0 || iw < 0 || id >= Di || ih >= Di || iw >= Di) continue;
                                 const __half* xp = &h_src[src][((((size_t)nb * Di + id) * Di + ih) * Di + iw) * C];
                                 const float* wp = &h_w[g][(size_t)co * cin * ks * ks * ks + (kd * ks + kh) * ks + kw];
-                                for (int ci = 0; ci < cin; ++ci)
-                                    acc += (double)__half2float(xp[ci]) * wp[(size_t)ci * ks * ks * ks];
+                                if (!c.f8corr) {
+                                    for (int ci = 0; ci < cin; ++ci)
+                                        acc += (double)__half2float(xp[ci]) * wp[(size_t)ci * ks * ks * ks];
+                                    continue;
+                                }
+                                // what the kernel is asked to compute: fp16(a) fp16(w) + A1 W1 + A2 W2 on the stored operands
+                                const size_t vrow = (((size_t)nb * Di + id) * Di + ih) * Di + iw;
+                                for (int ci = 0; ci < cin; ++ci) {
+                                    const float w = wp[(size_t)ci * ks * ks * ks], wh = __half2float(__float2half(w));
+                                    const uint8_t* row = &h_pair[src][(vrow * C + (size_t)(ci & ~63)) * 2];
+                                    const double a1 = e5m2f(row[ci & 63]), a2 = e5m2f(row[64 + (ci & 63)]);
+                                    const double w1 = e5m2f(e5m2(w * f8down)), w2 = e5m2f(e5m2((w - wh) * f8up));
+                                    const double hh = (double)__half2float(xp[ci]) * wh;
+                                    acc += hh + a1 * w1 + a2 * w2;
+                                    acc_h += hh;
+                                    acc_true += (double)h_true[src][vrow * C + ci] * w;
+                                }
                             }
                 }
                 const size_t oidx_nd = v * c.Cout + co;
@@ -230,6 +284,11 @@ int main(int argc, char** argv) {
                 const float got = h_out[oidx];
                 if (std::isnan(got)) { ++nan_cnt; continue; }
                 const double e = std::fabs(got - acc);
+                if (c.f8corr) {
+                    const double rr = c.residual ? h_res[oidx_nd] : 0.0;
+                    max_true_err = std::max(max_true_err, std::fabs(got - (acc_true + rr)));
+                    max_fp16_err = std::max(max_fp16_err, std::fabs(acc_h - acc_true));
+                }
                 max_err = std::max(max_err, e);
                 max_ref = std::max(max_ref, std::fabs(acc));
                 if (e > 2e-3 * std::max(1.0, std::fabs(acc))) ++bad;
@@ -266,6 +325,7 @@ int main(int argc, char** argv) {
         }
         const bool pass = (bad == 0 && nan_cnt == 0 && stats_bad == 0);
         printf("[%s] %s max_err=%.3e max_ref=%.3f bad=%zu nan=%zu\n", c.name.c_str(), pass ? "PASS" : "FAIL", max_err, max_ref, bad, nan_cnt);
+        if (c.f8corr) printf("[%s] vs exact a*w: fp16 pass + e5m2 corrections %.3e, single fp16 pass alone %.3e\n", c.name.c_str(), max_true_err, max_fp16_err);
         if (!pass) {
             ++n_fail;
             // print a few values to help diagnose layout errors
@@ -275,6 +335,7 @@ int main(int argc, char** argv) {
 
         conv_plan_destroy(plan);
         for (auto p : d_src) cudaFree(p);
+        for (auto p : d_pair) cudaFree(p);
         cudaFree(d_w); cudaFree(d_bias); cudaFree(d_res); cudaFree(d_out); cudaFree(d_stats);
     }
     printf("SUMMARY run=%d fail=%d\n", n_run, n_fail);

@@ -534,11 +534,14 @@ struct Mpm {
     float4* grid_v = nullptr;
     double* d_time = nullptr;          // direct path clock
     DevBC* d_bcs = nullptr;
-    // CUDA graph of a batch of substeps, keyed by dt and the state snapshot it was captured with
+    // direct path: CUDA graph of a batch of substeps, keyed by dt and the state snapshot it was captured with
     cudaGraphExec_t graph = nullptr;
     double graph_dt = 0;
     bool graph_valid = false;
-    int graph_parity = 0;
+    // fused path: a few cached graphs keyed by (substep count, clock parity, dt)
+    static constexpr int kGraphSlots = 4;
+    struct GraphSlot { cudaGraphExec_t exec = nullptr; int count = 0, parity = 0, launches = 0; double dt = 0; } graphs[kGraphSlots];
+    int graph_next = 0;
     std::string error;
 
     // ---- cell order (radix sort of base-cell keys): indirection of the direct path, physical order of the fused path
@@ -559,11 +562,22 @@ struct Mpm {
     bool internal_valid = false;       // sorted state mirrors the caller's arrays (+ steps taken since)
     bool user_stale = false;           // sorted state is ahead of the caller's arrays
     int steps_since_sort = 0;
-    int agg = 3;                       // log2 of the longest aggregated run in the scatter (PIXIE_MPM_AGG)
+    // ---- slab-decomposed runs on the fused path: exchange buffer = [SlabFlags][grid_mv], neighbours' buffers, overlap totals
+    uint8_t* xbuf = nullptr;           // owns grid_mv (+ the flags block in front of it): one allocation, one IPC handle
+    bool slab = false;
+    int slab_x0 = 0, slab_x1 = 0, slab_slack = 1;
+    const uint8_t* peer_xbuf[2] = {nullptr, nullptr};
+    float4* ov_total[2] = {nullptr, nullptr};
+    int ov_lo[2] = {0, 0}, ov_hi[2] = {0, 0};
+    bool g2p_pending = false;          // slab phases: the gather of the last finished substep has not run yet
+    float slab_dt = 0.f;               // ... and the dt it has to use
+    int agg = 2;                       // log2 of the longest aggregated run in the scatter (PIXIE_MPM_AGG): 2 measured best at 100k/64^3
+    long long launches = 0;            // kernels of this library launched for this handle (bench.py's gpu_launches)
 };
 
 static constexpr int kGraphSteps = 25;         // direct path
-static constexpr int kFusedGraphSteps = 50;    // fused path (even: the clock parity returns to where it started)
+static constexpr int kFusedGraphSteps = 50;    // fused path: substeps per graph replay
+static constexpr int kMinGraphSteps = 4;       // shorter batches are launched directly
 static constexpr int kResortEvery = 100;       // substeps between re-sorts; CFL keeps a particle within ~a cell of its slot far longer
 static constexpr int kBoxMargin = 2;           // nodes added around the particles' node box at every sort
 
@@ -595,6 +609,7 @@ static DevState make_state(Mpm* m) {
 
 void mpm_destroy(Mpm* m);
 int mpm_sync(Mpm* m, cudaStream_t st);
+static void fused_launch(Mpm* m, bool do_g2p, bool do_p2g, bool write_all, float dt, cudaStream_t st);
 
 // ---------------------------------------------------------------------------------- sort scratch (both paths)
 static int sort_alloc(Mpm* m) {
@@ -649,18 +664,22 @@ static void fused_box(Mpm* m, const float* x, long long stride_comp, long long s
     const int init[6] = {m->n_grid, m->n_grid, m->n_grid, 0, 0, 0};
     cudaMemcpyAsync(m->d_box, init, sizeof(init), cudaMemcpyHostToDevice, st);
     const float inv_dx = (float)((double)m->n_grid / (double)m->grid_lim);
-    fs_box_kernel<<<148, 256, 0, st>>>(x, stride_comp, stride_part, m->n, inv_dx, m->n_grid, kBoxMargin, m->d_box, 0);
-    fs_box_kernel<<<1, 32, 0, st>>>(x, stride_comp, stride_part, m->n, inv_dx, m->n_grid, kBoxMargin, m->d_box, 1);
+    fs_box_kernel<<<148, 256, 0, st>>>(x, stride_comp, stride_part, m->n_active, inv_dx, m->n_grid, kBoxMargin, m->d_box, 0);
+    fs_box_kernel<<<1, 32, 0, st>>>(x, stride_comp, stride_part, m->n_active, inv_dx, m->n_grid, kBoxMargin, m->d_box, 1);
+    m->launches += 2;
 }
 
 static int fused_sort(Mpm* m, const float* x, long long stride_comp, long long stride_part, cudaStream_t st) {
+    m->steps_since_sort = 0;
+    if (m->n_active <= 0) return 0;
     const float inv_dx = (float)((double)m->n_grid / (double)m->grid_lim);
-    fs_key_kernel<<<(m->n + 255) / 256, 256, 0, st>>>(x, stride_comp, stride_part, m->n, inv_dx, m->n_grid, m->cell_keys, m->cell_idx);
+    fs_key_kernel<<<(m->n_active + 255) / 256, 256, 0, st>>>(x, stride_comp, stride_part, m->n_active, inv_dx, m->n_grid, m->cell_keys, m->cell_idx);
     size_t bytes = m->cub_bytes;
-    if (cub::DeviceRadixSort::SortPairs(m->cub_tmp, bytes, m->cell_keys, m->cell_keys_sorted, m->cell_idx, m->cell_order, m->n, 0, key_bits(m), st) != cudaSuccess) {
+    if (cub::DeviceRadixSort::SortPairs(m->cub_tmp, bytes, m->cell_keys, m->cell_keys_sorted, m->cell_idx, m->cell_order, m->n_active, 0, key_bits(m), st) != cudaSuccess) {
         m->error = "radix sort failed"; return 1;
     }
     m->steps_since_sort = 0;
+    m->launches += 1;          // + the radix sort passes of cub (library kernels, not counted)
     return 0;
 }
 
@@ -670,9 +689,10 @@ static int fused_gather_from_user(Mpm* m, cudaStream_t st) {
     const FsUser u = fs_user(m);
     if (fused_sort(m, u.x, 1, 3, st)) return 1;
     Mpm::FsBuf& d = m->fs[0];
-    fs_gather_kernel<<<(m->n + 255) / 256, 256, 0, st>>>(u, m->cell_order, m->n, m->cap, d.f, d.material, d.selection, d.perm,
+    if (m->n_active > 0) fs_gather_kernel<<<(m->n_active + 255) / 256, 256, 0, st>>>(u, m->cell_order, m->n_active, m->cap, d.f, d.material, d.selection, d.perm,
                                                           m->params.update_cov_with_F ? 1 : 0);
     fused_box(m, u.x, 1, 3, st);
+    m->launches += 1;
     m->internal_valid = true;
     m->user_stale = false;
     return cudaGetLastError() != cudaSuccess;
@@ -683,7 +703,8 @@ static int fused_resort(Mpm* m, cudaStream_t st) {
     Mpm::FsBuf& a = m->fs[0];
     Mpm::FsBuf& b = m->fs[1];
     if (fused_sort(m, a.f + (size_t)FS_X * m->cap, m->cap, 1, st)) return 1;
-    fs_permute_kernel<<<(m->n + 255) / 256, 256, 0, st>>>(a.f, a.material, a.selection, a.perm, m->cell_order, m->n, m->cap, b.f, b.material,
+    if (m->n_active <= 0) return 0;
+    fs_permute_kernel<<<(m->n_active + 255) / 256, 256, 0, st>>>(a.f, a.material, a.selection, a.perm, m->cell_order, m->n_active, m->cap, b.f, b.material,
                                                            b.selection, b.perm);
     // back into buffer 0: the captured graph and the launch arguments keep pointing at it
     const size_t cap = (size_t)m->cap;
@@ -692,6 +713,7 @@ static int fused_resort(Mpm* m, cudaStream_t st) {
     cudaMemcpyAsync(a.selection, b.selection, cap * sizeof(int), cudaMemcpyDeviceToDevice, st);
     cudaMemcpyAsync(a.perm, b.perm, cap * sizeof(int), cudaMemcpyDeviceToDevice, st);
     fused_box(m, a.f + (size_t)FS_X * m->cap, m->cap, 1, st);
+    m->launches += 1;
     return cudaGetLastError() != cudaSuccess;
 }
 
@@ -699,25 +721,54 @@ static int fused_resort(Mpm* m, cudaStream_t st) {
 // considered out of date.
 int mpm_sync(Mpm* m, cudaStream_t st) {
     if (!m->fused) return 0;
+    if (m->g2p_pending && m->internal_valid) {        // slab phases: finish the last substep (gather) before anything is read
+        fused_launch(m, true, false, true, m->slab_dt, st);
+        m->g2p_pending = false;
+    }
     if (m->user_stale) {
         const Mpm::FsBuf& s = m->fs[0];
-        fs_unsort_kernel<<<(m->n + 255) / 256, 256, 0, st>>>(fs_user(m), s.perm, m->n, m->cap, s.f, m->params.update_cov_with_F ? 1 : 0);
+        if (m->n_active > 0) fs_unsort_kernel<<<(m->n_active + 255) / 256, 256, 0, st>>>(fs_user(m), s.perm, m->n_active, m->cap, s.f, m->params.update_cov_with_F ? 1 : 0);
         m->user_stale = false;
+        m->launches += 1;
         if (cudaGetLastError() != cudaSuccess) { m->error = "unsort launch failed"; return 1; }
     }
     m->internal_valid = false;
     return 0;
 }
 
+// Launch with programmatic stream serialisation (PDL): the kernel may be scheduled while its predecessor in the stream
+// (or captured graph) is still draining; both kernels of the substep chain wait for it with griddepcontrol.wait.
+template <typename... KArgs, typename... Args>
+static void pdl_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, Args... args) {
+    static const bool pdl = !(getenv("PIXIE_MPM_PDL") && atoi(getenv("PIXIE_MPM_PDL")) == 0);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 static FusedState fused_state(Mpm* m) {
     FusedState t{};
     const Mpm::FsBuf& s = m->fs[0];
     t.f = s.f; t.material = s.material; t.selection = s.selection; t.perm = s.perm;
-    t.cap = m->cap; t.n = m->n;
+    t.cap = m->cap; t.n = m->n_active;
     t.grid_v = m->grid_v; t.grid_mv = m->grid_mv; t.box = m->d_box;
     t.bcs = m->d_bcs; t.n_bc = (int)m->bcs.size();
     t.n_particle_bc = 0;
-    for (const DevBC& b : m->bcs) t.n_particle_bc += b.kind >= PIXIE_BC_IMPULSE ? 1 : 0;
+    for (const DevBC& b : m->bcs) {
+        if (b.kind < PIXIE_BC_IMPULSE) continue;
+        if (t.n_particle_bc < kInlinePBC) {
+            ParticleBC& q = t.pbc[t.n_particle_bc];
+            q.kind = b.kind; q.start_time = b.start_time; q.end_time = b.end_time; q.mask = b.mask;
+            q.rotation_scale = b.rotation_scale; q.translation_scale = b.translation_scale;
+            for (int a = 0; a < 3; ++a) { q.velocity[a] = b.velocity[a]; q.point[a] = b.point[a]; q.normal[a] = b.normal[a]; q.h1[a] = b.h1[a]; q.h2[a] = b.h2[a]; }
+        }
+        ++t.n_particle_bc;
+    }
+    t.n_pbc_inline = t.n_particle_bc <= kInlinePBC ? t.n_particle_bc : -1;
     t.n_grid = m->n_grid;
     t.dx = (float)((double)m->grid_lim / (double)m->n_grid);
     t.inv_dx = (float)((double)m->n_grid / (double)m->grid_lim);
@@ -732,13 +783,15 @@ static void fused_launch(Mpm* m, bool do_g2p, bool do_p2g, bool write_all, float
     FusedState t = fused_state(m);
     t.do_g2p = do_g2p; t.do_p2g = do_p2g; t.write_all = write_all;
     t.time = m->tslots + m->tpar;                 // clock of the substep whose stress / scatter runs in this launch
-    const int blocks = (m->n + kFusedThreads - 1) / kFusedThreads;
-    switch (m->agg) {
-        case 0: mpm_fused_kernel<0><<<blocks, kFusedThreads, 0, st>>>(t, dt); break;
-        case 1: mpm_fused_kernel<1><<<blocks, kFusedThreads, 0, st>>>(t, dt); break;
-        case 2: mpm_fused_kernel<2><<<blocks, kFusedThreads, 0, st>>>(t, dt); break;
-        default: mpm_fused_kernel<3><<<blocks, kFusedThreads, 0, st>>>(t, dt); break;
-    }
+    // 88 registers per thread: 32-thread blocks pack 23 per SM (736 threads), so 100k particles are one wave on 148 SMs
+    static const int B = [] { const char* e = getenv("PIXIE_MPM_FUSED_BLOCK"); const int b = e ? atoi(e) : kFusedThreads; return (b == 32 || b == 64 || b == 128) ? b : kFusedThreads; }();
+    const int blocks = (std::max(m->n_active, 1) + B - 1) / B;
+    static const bool hoist = !(getenv("PIXIE_MPM_HOIST") && atoi(getenv("PIXIE_MPM_HOIST")) == 0);   // r02 A/B: 23.5 vs 24.1 us
+    void (*kern)(const FusedState, const float) = mpm_fused_kernel<2, false>;
+    if (hoist) kern = m->agg == 1 ? mpm_fused_kernel<1, true> : (m->agg == 3 ? mpm_fused_kernel<3, true> : mpm_fused_kernel<2, true>);
+    else kern = m->agg == 0 ? mpm_fused_kernel<0, false> : (m->agg == 1 ? mpm_fused_kernel<1, false> : (m->agg == 3 ? mpm_fused_kernel<3, false> : mpm_fused_kernel<2, false>));
+    pdl_launch(kern, dim3(blocks), dim3(B), st, t, dt);
+    m->launches += 1;
 }
 
 static void gridbox_launch(Mpm* m, float dt, double dt_d, cudaStream_t st) {
@@ -748,60 +801,95 @@ static void gridbox_launch(Mpm* m, float dt, double dt_d, cudaStream_t st) {
     g.pts_in = m->pts + (size_t)m->tpar * kMaxBC * 3; g.pts_out = m->pts + (size_t)(m->tpar ^ 1) * kMaxBC * 3;
     g.bcs = m->d_bcs; g.n_bc = (int)m->bcs.size();
     g.n_grid = m->n_grid; g.x_begin = m->x_begin; g.x_end = m->x_end;
+    if (m->slab) {
+        g.mine = reinterpret_cast<SlabFlags*>(m->xbuf);
+        for (int sd = 0; sd < 2; ++sd) {
+            g.peer[sd] = reinterpret_cast<const SlabFlags*>(m->peer_xbuf[sd]);
+            g.total[sd] = m->ov_total[sd]; g.ov_lo[sd] = m->ov_lo[sd]; g.ov_hi[sd] = m->ov_hi[sd];
+        }
+    }
     g.dx = (float)((double)m->grid_lim / (double)m->n_grid);
     const pixie_mpm_params& q = m->params;
     g.gx = q.gravity[0]; g.gy = q.gravity[1]; g.gz = q.gravity[2]; g.grid_v_damping_scale = q.grid_v_damping_scale;
     // enough blocks for two per SM; the kernel strides over the (usually much smaller than n_grid^3) node box
-    mpm_gridbox_kernel<<<296, 256, 0, st>>>(g, dt, dt_d);
+    pdl_launch(mpm_gridbox_kernel, dim3(296), dim3(256), st, g, dt, dt_d);
+    m->launches += 1;
     m->tpar ^= 1;
 }
 
-// `count` substeps as: scatter(0) | grid(0) | g2p(0)+scatter(1) | ... | grid(count-1) | g2p(count-1)
+static void halo_launch(Mpm* m, cudaStream_t st) {
+    HaloArgs a{};
+    a.mine = reinterpret_cast<SlabFlags*>(m->xbuf);
+    a.grid_mv = m->grid_mv; a.box = m->d_box; a.n_grid = m->n_grid;
+    for (int sd = 0; sd < 2; ++sd) {
+        a.peer[sd] = reinterpret_cast<const SlabFlags*>(m->peer_xbuf[sd]);
+        a.peer_mv[sd] = m->peer_xbuf[sd] ? reinterpret_cast<const float4*>(m->peer_xbuf[sd] + sizeof(SlabFlags)) : nullptr;
+        a.total[sd] = m->ov_total[sd]; a.ov_lo[sd] = m->ov_lo[sd]; a.ov_hi[sd] = m->ov_hi[sd];
+    }
+    pdl_launch(mpm_halo_kernel, dim3(148), dim3(256), st, a);
+    m->launches += 1;
+}
+
+// `count` substeps as: scatter(0) | [halo(0)] | grid(0) | g2p(0)+scatter(1) | ... | grid(count-1) | g2p(count-1)
 static void fused_batch(Mpm* m, int count, float dt, double dt_d, cudaStream_t st) {
-    fused_launch(m, false, true, count == 1, dt, st);
+    fused_launch(m, false, true, count == 1 || m->slab, dt, st);
     for (int i = 0; i < count; ++i) {
+        if (m->slab) halo_launch(m, st);
         gridbox_launch(m, dt, dt_d, st);
-        if (i + 1 < count) fused_launch(m, true, true, i + 2 == count, dt, st);
+        if (i + 1 < count) fused_launch(m, true, true, i + 2 == count || m->slab, dt, st);
         else fused_launch(m, true, false, true, dt, st);
     }
+}
+
+// CUDA graph of `count` substeps starting at clock parity `m->tpar` (cached: the 50-substep batch of long rollouts and, for
+// slab runs, the chunk between two particle migrations)
+static cudaGraphExec_t fused_graph(Mpm* m, int count, float dt, double dt_d) {
+    for (auto& g : m->graphs)
+        if (g.exec && g.count == count && g.parity == m->tpar && g.dt == dt_d) return g.exec;
+    Mpm::GraphSlot& slot = m->graphs[m->graph_next];
+    m->graph_next = (m->graph_next + 1) % Mpm::kGraphSlots;
+    if (slot.exec) { cudaGraphExecDestroy(slot.exec); slot.exec = nullptr; }
+    cudaStream_t cs;
+    cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking);
+    cudaGraph_t g = nullptr;
+    const int par0 = m->tpar;
+    const long long launches0 = m->launches;
+    bool ok = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+    if (ok) {
+        fused_batch(m, count, dt, dt_d, cs);
+        ok = cudaStreamEndCapture(cs, &g) == cudaSuccess && g;
+    }
+    slot.launches = (int)(m->launches - launches0);
+    m->tpar = par0;                                    // capture did not run anything
+    m->launches = launches0;
+    if (ok) ok = cudaGraphInstantiate(&slot.exec, g, 0) == cudaSuccess;
+    if (g) cudaGraphDestroy(g);
+    cudaStreamDestroy(cs);
+    if (!ok) { cudaGetLastError(); slot.exec = nullptr; return nullptr; }
+    slot.count = count; slot.parity = par0; slot.dt = dt_d;
+    return slot.exec;
 }
 
 static int mpm_step_fused(Mpm* m, int n_substeps, double dt_d, cudaStream_t st) {
     const float dt = (float)dt_d;
     if (!m->internal_valid && fused_gather_from_user(m, st)) return 1;
-    int done = 0;
-    if (n_substeps >= kFusedGraphSteps) {
-        if (!m->graph_valid || m->graph_dt != dt_d || m->graph_parity != m->tpar) {
-            if (m->graph) { cudaGraphExecDestroy(m->graph); m->graph = nullptr; }
-            cudaStream_t cs;
-            cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking);
-            cudaGraph_t g = nullptr;
-            const int par0 = m->tpar;
-            bool ok = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
-            if (ok) {
-                fused_batch(m, kFusedGraphSteps, dt, dt_d, cs);
-                ok = cudaStreamEndCapture(cs, &g) == cudaSuccess && g;
-            }
-            m->tpar = par0;                                    // capture did not run anything
-            if (ok) ok = cudaGraphInstantiate(&m->graph, g, 0) == cudaSuccess;
-            if (g) cudaGraphDestroy(g);
-            cudaStreamDestroy(cs);
-            if (!ok) { cudaGetLastError(); m->graph = nullptr; }
-            m->graph_valid = ok;
-            m->graph_dt = dt_d;
-            m->graph_parity = par0;
-        }
-        while (m->graph_valid && n_substeps - done >= kFusedGraphSteps) {
-            if (m->steps_since_sort >= kResortEvery && fused_resort(m, st)) return 1;
-            if (cudaGraphLaunch(m->graph, st) != cudaSuccess) { m->error = "cudaGraphLaunch failed"; return 1; }
-            done += kFusedGraphSteps;                          // even number of substeps: the parity is back at graph_parity
-            m->steps_since_sort += kFusedGraphSteps;
-        }
+    if (!m->graph_valid) {                              // parameters / BCs / bindings changed: captured launches are stale
+        for (auto& g : m->graphs) if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+        m->graph_valid = true;
     }
+    int done = 0;
     while (done < n_substeps) {
         if (m->steps_since_sort >= kResortEvery && fused_resort(m, st)) return 1;
-        const int count = std::min(n_substeps - done, kResortEvery);
-        fused_batch(m, count, dt, dt_d, st);
+        int count = std::min(n_substeps - done, kFusedGraphSteps);
+        count = std::min(count, std::max(1, kResortEvery - m->steps_since_sort));
+        cudaGraphExec_t g = count >= kMinGraphSteps ? fused_graph(m, count, dt, dt_d) : nullptr;
+        if (g) {
+            if (cudaGraphLaunch(g, st) != cudaSuccess) { m->error = "cudaGraphLaunch failed"; return 1; }
+            for (auto& sl : m->graphs) if (sl.exec == g) m->launches += sl.launches;
+            if (count & 1) m->tpar ^= 1;               // the replay advanced the clock `count` times
+        } else {
+            fused_batch(m, count, dt, dt_d, st);
+        }
         done += count;
         m->steps_since_sort += count;
     }
@@ -845,7 +933,7 @@ Mpm* mpm_create(int n_particles, int n_grid, float grid_lim, std::string& err) {
     }
     m->params.softening = 0.1f;
     const size_t nodes = (size_t)n_grid * n_grid * n_grid;
-    if (cudaMalloc(&m->grid_mv, nodes * sizeof(float4)) != cudaSuccess ||
+    if (cudaMalloc(&m->xbuf, sizeof(SlabFlags) + nodes * sizeof(float4)) != cudaSuccess ||
         cudaMalloc(&m->grid_v, nodes * sizeof(float4)) != cudaSuccess ||
         cudaMalloc(&m->d_time, sizeof(double)) != cudaSuccess ||
         cudaMalloc(&m->d_bcs, kMaxBC * sizeof(DevBC)) != cudaSuccess ||
@@ -856,7 +944,8 @@ Mpm* mpm_create(int n_particles, int n_grid, float grid_lim, std::string& err) {
         delete m;
         return nullptr;
     }
-    cudaMemset(m->grid_mv, 0, nodes * sizeof(float4));
+    m->grid_mv = reinterpret_cast<float4*>(m->xbuf + sizeof(SlabFlags));
+    cudaMemset(m->xbuf, 0, sizeof(SlabFlags) + nodes * sizeof(float4));
     cudaMemset(m->grid_v, 0, nodes * sizeof(float4));
     cudaMemset(m->d_time, 0, sizeof(double));
     cudaMemset(m->tslots, 0, 2 * sizeof(double));
@@ -872,7 +961,9 @@ void mpm_destroy(Mpm* m) {
     for (int b = 0; b < 2; ++b) { cudaFree(m->fs[b].f); cudaFree(m->fs[b].material); cudaFree(m->fs[b].selection); cudaFree(m->fs[b].perm); }
     cudaFree(m->d_box); cudaFree(m->tslots); cudaFree(m->pts);
     if (m->graph) cudaGraphExecDestroy(m->graph);
-    if (!m->grid_borrowed) cudaFree(m->grid_mv);
+    for (auto& g : m->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+    cudaFree(m->xbuf);
+    cudaFree(m->ov_total[0]); cudaFree(m->ov_total[1]);
     cudaFree(m->grid_v); cudaFree(m->d_time); cudaFree(m->d_bcs);
     delete m;
 }
@@ -888,12 +979,16 @@ int mpm_set_params(Mpm* m, const pixie_mpm_params& p) {
     if (mpm_sync(m, 0)) return 1;
     if (p.n_grid != m->n_grid) {
         // set_parameters_dict re-allocates the grids when n_grid changes (mpm_solver_warp.py:318-343)
+        if (m->slab) { m->error = "n_grid cannot change in slab mode"; return 1; }
         cudaDeviceSynchronize();
-        cudaFree(m->grid_mv); cudaFree(m->grid_v);
+        if (!m->grid_borrowed) cudaFree(m->xbuf);
+        cudaFree(m->grid_v);
+        m->xbuf = nullptr; m->grid_borrowed = false;
         const size_t nodes = (size_t)p.n_grid * p.n_grid * p.n_grid;
-        if (cudaMalloc(&m->grid_mv, nodes * sizeof(float4)) != cudaSuccess ||
+        if (cudaMalloc(&m->xbuf, sizeof(SlabFlags) + nodes * sizeof(float4)) != cudaSuccess ||
             cudaMalloc(&m->grid_v, nodes * sizeof(float4)) != cudaSuccess) { m->error = "cudaMalloc failed"; return 1; }
-        cudaMemset(m->grid_mv, 0, nodes * sizeof(float4));
+        m->grid_mv = reinterpret_cast<float4*>(m->xbuf + sizeof(SlabFlags));
+        cudaMemset(m->xbuf, 0, sizeof(SlabFlags) + nodes * sizeof(float4));
         cudaMemset(m->grid_v, 0, nodes * sizeof(float4));
         m->n_grid = p.n_grid;
         m->x_begin = 0; m->x_end = p.n_grid;
@@ -1015,11 +1110,12 @@ int mpm_step(Mpm* m, int n_substeps, double dt_d, cudaStream_t st) {
                 if (m->steps_since_order >= kReorderEvery && mpm_build_cell_order(m, st)) return 1;
                 if (cudaGraphLaunch(m->graph, st) != cudaSuccess) { m->error = "cudaGraphLaunch failed"; return 1; }
                 done += kGraphSteps;
+                m->launches += 4 * kGraphSteps;
                 m->steps_since_order += kGraphSteps;
             }
         }
     }
-    for (; done < n_substeps; ++done) { launch_substep(s, dt, dt_d, st); ++m->steps_since_order; }
+    for (; done < n_substeps; ++done) { launch_substep(s, dt, dt_d, st); ++m->steps_since_order; m->launches += 4; }
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { m->error = std::string("kernel launch failed: ") + cudaGetErrorString(e); return 1; }
     return 0;
@@ -1071,8 +1167,7 @@ int mpm_select_cylinder(Mpm* m, const float* point, const float* normal, float h
 //      scatter and finish, and migrates particles by shrinking / growing the live prefix of the bound arrays.
 int mpm_bind_grid(Mpm* m, void* mv4) {
     if (switch_to_direct(m)) return 1;
-    if (!m->grid_borrowed) cudaFree(m->grid_mv);
-    m->grid_mv = reinterpret_cast<float4*>(mv4);
+    m->grid_mv = reinterpret_cast<float4*>(mv4);            // the handle's own buffer (xbuf) stays allocated, unused
     m->grid_borrowed = true;
     m->graph_valid = false;
     return 0;
@@ -1086,7 +1181,7 @@ int mpm_set_slab(Mpm* m, int x_begin, int x_end) {
 }
 int mpm_set_active_count(Mpm* m, int n_active) {
     if (n_active < 0 || n_active > m->n) { m->error = "active count exceeds the bound capacity"; return 1; }
-    if (switch_to_direct(m)) return 1;
+    if (mpm_sync(m, 0)) return 1;          // results of the old live prefix go back first; the next step re-reads the arrays
     m->n_active = n_active;
     m->order_valid = false;       // the order lists exactly the live prefix
     m->graph_valid = false;
@@ -1112,11 +1207,73 @@ int mpm_substep_finish(Mpm* m, double dt_d, cudaStream_t st) {
     mpm_g2p_kernel<<<(std::max(s.n, 1) + particle_block() - 1) / particle_block(), particle_block(), 0, st>>>(s, (float)dt_d, dt_d);
     return cudaGetLastError() != cudaSuccess;
 }
+// ---- slab mode of the fused path (BASELINE config 5). The exchange buffer [SlabFlags][grid_mv] of each handle is made
+//      visible to its x-neighbours (cudaIpc between processes, plain pointers inside one process); scatter, overlap
+//      exchange and grid update then chain on the device with flag handshakes, no host in the loop.
+int mpm_exchange_buffer(Mpm* m, void** base, size_t* bytes) {
+    *base = m->xbuf;
+    *bytes = sizeof(SlabFlags) + (size_t)m->n_grid * m->n_grid * m->n_grid * sizeof(float4);
+    return 0;
+}
+int mpm_slab_attach(Mpm* m, int x0, int x1, int slack, const void* left_xbuf, const void* right_xbuf) {
+    if (!m->fused) { m->error = "slab_attach needs the default (fused) path"; return 1; }
+    if (x0 < 0 || x1 > m->n_grid || x0 >= x1 || slack < 0) { m->error = "bad slab range"; return 1; }
+    if ((left_xbuf || right_xbuf) && (x1 - x0) < 2 + 2 * slack) { m->error = "slab narrower than 2 + 2*slack planes"; return 1; }
+    if (mpm_sync(m, 0)) return 1;
+    const int n = m->n_grid;
+    m->slab = true; m->slab_x0 = x0; m->slab_x1 = x1; m->slab_slack = slack;
+    m->peer_xbuf[0] = reinterpret_cast<const uint8_t*>(left_xbuf);
+    m->peer_xbuf[1] = reinterpret_cast<const uint8_t*>(right_xbuf);
+    // planes shared with a neighbour: both of them touch [x - slack, x + 2 + slack) around the interface x
+    m->ov_lo[0] = std::max(0, x0 - slack); m->ov_hi[0] = std::min(n, x0 + 2 + slack);
+    m->ov_lo[1] = std::max(0, x1 - slack); m->ov_hi[1] = std::min(n, x1 + 2 + slack);
+    m->x_begin = left_xbuf ? m->ov_lo[0] : 0;
+    m->x_end = right_xbuf ? m->ov_hi[1] : n;
+    for (int sd = 0; sd < 2; ++sd) {
+        cudaFree(m->ov_total[sd]); m->ov_total[sd] = nullptr;
+        if (!m->peer_xbuf[sd]) continue;
+        const size_t bytes = (size_t)(m->ov_hi[sd] - m->ov_lo[sd]) * n * n * sizeof(float4);
+        if (cudaMalloc(&m->ov_total[sd], bytes) != cudaSuccess) { m->error = "cudaMalloc failed (overlap totals)"; return 1; }
+        cudaMemset(m->ov_total[sd], 0, bytes);
+    }
+    cudaMemset(m->xbuf, 0, sizeof(SlabFlags));
+    m->graph_valid = false;
+    m->g2p_pending = false;
+    return 0;
+}
+// One phase of a substep (single-process drivers sequence the phases of all slabs; a multi-process rank calls mpm_step).
+int mpm_slab_phase(Mpm* m, int phase, double dt_d, cudaStream_t st) {
+    if (!m->slab) { m->error = "not in slab mode"; return 1; }
+    if (check_bound(m)) return 1;
+    const float dt = (float)dt_d;
+    if (phase == 0) {
+        if (!m->internal_valid) { if (fused_gather_from_user(m, st)) return 1; m->g2p_pending = false; }
+        else if (m->steps_since_sort >= kResortEvery && fused_resort(m, st)) return 1;
+        fused_launch(m, m->g2p_pending, true, true, dt, st);
+        m->g2p_pending = false;
+    } else if (phase == 1) {
+        halo_launch(m, st);
+    } else if (phase == 2) {
+        gridbox_launch(m, dt, dt_d, st);
+        m->g2p_pending = true; m->slab_dt = dt;
+        ++m->steps_since_sort;
+        m->user_stale = true;
+    } else { m->error = "bad phase"; return 1; }
+    return cudaGetLastError() != cudaSuccess;
+}
+int mpm_slab_error(Mpm* m, int* flag) {
+    SlabFlags f{};
+    if (cudaMemcpy(&f, m->xbuf, sizeof(f), cudaMemcpyDeviceToHost) != cudaSuccess) return 1;
+    *flag = f.error;
+    return 0;
+}
+
 int mpm_grid_ptrs(Mpm* m, float** mv4, float** v4) {
     *mv4 = reinterpret_cast<float*>(m->grid_mv);
     *v4 = reinterpret_cast<float*>(m->grid_v);
     return 0;
 }
+long long mpm_launch_count(Mpm* m) { return m->launches; }
 const std::string& mpm_error(Mpm* m) { return m->error; }
 
 }  // namespace pixie

@@ -30,5 +30,10 @@ int mpm_set_slab(Mpm* m, int x_begin, int x_end);
 int mpm_set_active_count(Mpm* m, int n_active);
 int mpm_substep_scatter(Mpm* m, double dt, cudaStream_t st);
 int mpm_substep_finish(Mpm* m, double dt, cudaStream_t st);
+long long mpm_launch_count(Mpm* m);
+int mpm_exchange_buffer(Mpm* m, void** base, size_t* bytes);
+int mpm_slab_attach(Mpm* m, int x0, int x1, int slack, const void* left_xbuf, const void* right_xbuf);
+int mpm_slab_phase(Mpm* m, int phase, double dt, cudaStream_t st);
+int mpm_slab_error(Mpm* m, int* flag);
 const std::string& mpm_error(Mpm* m);
 }  // namespace pixie

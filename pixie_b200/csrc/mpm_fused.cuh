@@ -22,11 +22,22 @@
 // mpm_solver_warp.py:528-547 (particle BCs), :785-974 (grid BCs), :899-905 + :637 (moving cuboid, clock).
 #pragma once
 
-constexpr int kFusedThreads = 64;
+constexpr int kFusedThreads = 32;
 
 // component rows of the SoA buffer (floats)
 enum : int { FS_X = 0, FS_V = 3, FS_C = 6, FS_F = 15, FS_FT = 24, FS_TAU = 33, FS_MASS = 42, FS_VOL = 43, FS_MU = 44, FS_LAM = 45,
              FS_BULK = 46, FS_YS = 47, FS_COV = 48, FS_NFLOAT = 54 };
+
+constexpr int kInlinePBC = 4;       // particle BCs (impulses / velocity modifiers) carried in the kernel parameters
+
+struct ParticleBC {                 // what apply_force / modify_particle_v_before_p2g read (mpm_solver_warp.py:1004-1179)
+    int kind;
+    float start_time, end_time;
+    float velocity[3];              // force for impulses
+    float point[3], normal[3], h1[3], h2[3];
+    float rotation_scale, translation_scale;
+    const int* mask;
+};
 
 struct FusedState {
     float* f;                       // [FS_NFLOAT][cap]
@@ -39,11 +50,19 @@ struct FusedState {
     const double* time;             // clock of the substep whose stress / p2g run in this launch
     const DevBC* bcs;
     int n_bc, n_particle_bc;
+    int n_pbc_inline;               // >= 0: the particle BCs are pbc[0..n); -1: more than kInlinePBC, walk the device table
+    ParticleBC pbc[kInlinePBC];
     int n_grid;
     float dx, inv_dx;
     float rpic_damping, alpha, hardening, xi, plastic_viscosity, softening;
     int update_cov_with_F;
     int do_g2p, do_p2g, write_all;
+    // slab-decomposed runs (one scene over several GPUs): substep counter that the exchange kernels key their flags on, and
+    // the plane range a particle's stencil base may lie in (owned planes +- slack); outside it the scatter would reach planes
+    // that are neither exchanged nor swept, so the kernel raises the error flag instead
+    int* slab_step;                 // nullptr outside slab mode
+    int* slab_err;
+    int base_lo, base_hi;
 };
 
 struct AxisW { float w0, w1, w2, d0, d1, d2, fx; int b; };   // weights, derivative weights (without inv_dx), offset, base
@@ -144,61 +163,111 @@ __device__ __noinline__ void fcr_svd_fallback(const M3& F, float J, float mu, fl
 }
 
 // ---- pre-p2g particle operations: all impulses first, then all velocity modifiers (mpm_solver_warp.py:528-547)
+template <class BC>
+__device__ __forceinline__ void apply_impulse(const BC& bc, int orig, float time, float dt, float mass, float& vx, float& vy, float& vz, bool& dirty) {
+    if (time >= bc.start_time && time < bc.end_time && bc.mask[orig] == 1) {
+        vx = vx + (bc.velocity[0] / mass) * dt;          // apply_force :1015-1027 (force stored in velocity[])
+        vy = vy + (bc.velocity[1] / mass) * dt;
+        vz = vz + (bc.velocity[2] / mass) * dt;
+        dirty = true;
+    }
+}
+template <class BC>
+__device__ __forceinline__ void apply_modifier(const BC& bc, int orig, float time, float px, float py, float pz, float& vx, float& vy, float& vz,
+                                               bool& dirty) {
+    if (!(time >= bc.start_time && time < bc.end_time) || bc.mask[orig] != 1) return;
+    if (bc.kind == PIXIE_BC_VELOCITY_TRANSLATION) {
+        vx = bc.velocity[0]; vy = bc.velocity[1]; vz = bc.velocity[2];
+    } else {                                                                             // rotation :1137-1179
+        const float ox = px - bc.point[0], oy = py - bc.point[1], oz = pz - bc.point[2];
+        const float on = ox * bc.normal[0] + oy * bc.normal[1] + oz * bc.normal[2];
+        const float hx = ox - on * bc.normal[0], hy = oy - on * bc.normal[1], hz = oz - on * bc.normal[2];
+        const float hd = sqrtf(hx * hx + hy * hy + hz * hz);
+        const float cosine = (ox * bc.h1[0] + oy * bc.h1[1] + oz * bc.h1[2]) / hd;
+        float theta = acosf(cosine);
+        if (!(ox * bc.h2[0] + oy * bc.h2[1] + oz * bc.h2[2] > 0.f)) theta = -theta;
+        const float a1 = -hd * sinf(theta) * bc.rotation_scale;
+        const float a2 = hd * cosf(theta) * bc.rotation_scale;
+        const float av = bc.translation_scale;
+        vx = a1 * bc.h1[0] + a2 * bc.h2[0] + av * bc.normal[0];
+        vy = a1 * bc.h1[1] + a2 * bc.h2[1] + av * bc.normal[1];
+        vz = a1 * bc.h1[2] + a2 * bc.h2[2] + av * bc.normal[2];
+    }
+    dirty = true;
+}
+
 __device__ __noinline__ bool particle_bcs(const FusedState& s, int orig, float time, float dt, float mass, float px, float py, float pz,
                                           float& vx, float& vy, float& vz) {
     bool dirty = false;
-    for (int k = 0; k < s.n_bc; ++k) {
-        const DevBC& bc = s.bcs[k];
-        if (bc.kind != PIXIE_BC_IMPULSE) continue;
-        if (time >= bc.start_time && time < bc.end_time && bc.mask[orig] == 1) {
-            vx = vx + (bc.velocity[0] / mass) * dt;          // apply_force :1015-1027 (force stored in velocity[])
-            vy = vy + (bc.velocity[1] / mass) * dt;
-            vz = vz + (bc.velocity[2] / mass) * dt;
-            dirty = true;
-        }
+    if (s.n_pbc_inline >= 0) {                       // descriptors in the constant bank: no table loads
+        for (int k = 0; k < s.n_pbc_inline; ++k)
+            if (s.pbc[k].kind == PIXIE_BC_IMPULSE) apply_impulse(s.pbc[k], orig, time, dt, mass, vx, vy, vz, dirty);
+        for (int k = 0; k < s.n_pbc_inline; ++k)
+            if (s.pbc[k].kind != PIXIE_BC_IMPULSE) apply_modifier(s.pbc[k], orig, time, px, py, pz, vx, vy, vz, dirty);
+        return dirty;
     }
     for (int k = 0; k < s.n_bc; ++k) {
         const DevBC& bc = s.bcs[k];
-        if (bc.kind == PIXIE_BC_VELOCITY_TRANSLATION) {
-            if (time >= bc.start_time && time < bc.end_time && bc.mask[orig] == 1) {
-                vx = bc.velocity[0]; vy = bc.velocity[1]; vz = bc.velocity[2];
-                dirty = true;
-            }
-        } else if (bc.kind == PIXIE_BC_VELOCITY_ROTATION) {
-            if (time >= bc.start_time && time < bc.end_time && bc.mask[orig] == 1) {     // :1137-1179
-                const float ox = px - bc.point[0], oy = py - bc.point[1], oz = pz - bc.point[2];
-                const float on = ox * bc.normal[0] + oy * bc.normal[1] + oz * bc.normal[2];
-                const float hx = ox - on * bc.normal[0], hy = oy - on * bc.normal[1], hz = oz - on * bc.normal[2];
-                const float hd = sqrtf(hx * hx + hy * hy + hz * hz);
-                const float cosine = (ox * bc.h1[0] + oy * bc.h1[1] + oz * bc.h1[2]) / hd;
-                float theta = acosf(cosine);
-                if (!(ox * bc.h2[0] + oy * bc.h2[1] + oz * bc.h2[2] > 0.f)) theta = -theta;
-                const float a1 = -hd * sinf(theta) * bc.rotation_scale;
-                const float a2 = hd * cosf(theta) * bc.rotation_scale;
-                const float av = bc.translation_scale;
-                vx = a1 * bc.h1[0] + a2 * bc.h2[0] + av * bc.normal[0];
-                vy = a1 * bc.h1[1] + a2 * bc.h2[1] + av * bc.normal[1];
-                vz = a1 * bc.h1[2] + a2 * bc.h2[2] + av * bc.normal[2];
-                dirty = true;
-            }
-        }
+        if (bc.kind == PIXIE_BC_IMPULSE) apply_impulse(bc, orig, time, dt, mass, vx, vy, vz, dirty);
+    }
+    for (int k = 0; k < s.n_bc; ++k) {
+        const DevBC& bc = s.bcs[k];
+        if (bc.kind == PIXIE_BC_VELOCITY_TRANSLATION || bc.kind == PIXIE_BC_VELOCITY_ROTATION) apply_modifier(bc, orig, time, px, py, pz, vx, vy, vz, dirty);
     }
     return dirty;
 }
 
+// true when some particle BC's time window contains `time` (uniform over the grid: one test per thread, no mask loads)
+__device__ __forceinline__ bool any_particle_bc_active(const FusedState& s, float time) {
+    if (s.n_pbc_inline < 0) return true;
+    bool any = false;
+    for (int k = 0; k < s.n_pbc_inline; ++k) any = any || (time >= s.pbc[k].start_time && time < s.pbc[k].end_time);
+    return any;
+}
+
 // AGG = log2 of the longest run of equal-cell lanes that is summed before one red is issued (0: no aggregation)
-template <int AGG>
-__global__ void __launch_bounds__(kFusedThreads, 11)
-mpm_fused_kernel(const FusedState s, const float dt) {
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
+// HOIST: issue the late-needed per-particle loads at the top (costs registers across the gather); otherwise only prefetch
+// their lines into L1 there and load at the point of use
+template <int AGG, bool HOIST>
+__global__ void __maxnreg__(88)
+mpm_fused_kernel(const __grid_constant__ FusedState s, const float dt) {
+    // programmatic dependent launch: let the next kernel of the chain get scheduled while this one runs, and wait here
+    // for the previous one (its grid velocities / the particle state it wrote) — no-ops in a plain launch
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    // slab mode: one scattering launch per substep advances the substep counter (nothing in THIS launch reads it; the halo
+    // and grid kernels behind it in the stream do)
+    if (s.slab_step && s.do_p2g && blockIdx.x == 0 && threadIdx.x == 0) *s.slab_step = *s.slab_step + 1;
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = tid < s.n;
-    const int p = live ? tid : s.n - 1;                       // whole warps stay converged for the shuffles
+    const int p = live ? tid : max(s.n - 1, 0);               // whole warps stay converged for the shuffles
     const size_t cap = (size_t)s.cap;
     float* __restrict__ f = s.f;
     const bool act = live && s.selection[p] == 0;
     const int n = s.n_grid;
 
+    // every load whose address is known up front is issued here, back to back: with ~5 warps per scheduler each dependent
+    // trip to L2 that is taken alone costs the warp ~300 idle cycles (r02 ncu: 40 % of the stall samples were long-scoreboard)
     float px = f[(FS_X + 0) * cap + p], py = f[(FS_X + 1) * cap + p], pz = f[(FS_X + 2) * cap + p];
+    float mass, vol, mu, lam, time = 0.f;
+    int material, orig = 0;
+    int box[6];
+    auto late_loads = [&]() {
+        mass = f[FS_MASS * cap + p]; vol = f[FS_VOL * cap + p];
+        mu = f[FS_MU * cap + p]; lam = f[FS_LAM * cap + p];
+        material = s.material[p];
+        if (s.n_particle_bc > 0) { orig = s.perm[p]; time = (float)(*s.time); }
+#pragma unroll
+        for (int k = 0; k < 6; ++k) box[k] = s.box[k];
+    };
+    if (HOIST) late_loads();
+    else if ((threadIdx.x & 31) == 0) {           // one lane per warp pulls the warp's lines (128 B = 32 particles) into L1
+        prefetch_l1(f + FS_MASS * cap + p); prefetch_l1(f + FS_VOL * cap + p); prefetch_l1(f + FS_MU * cap + p);
+        prefetch_l1(f + FS_LAM * cap + p); prefetch_l1(s.material + p); prefetch_l1(s.box);
+        if (s.n_particle_bc > 0) prefetch_l1(s.perm + p);
+    }
     float vx, vy, vz;
     M3 C, Ft;
 
@@ -260,16 +329,12 @@ mpm_fused_kernel(const FusedState s, const float dt) {
     }
 
     // ---------------------------------------------------------------------- particle BCs, stress (substep i+1)
-    const float mass = f[FS_MASS * cap + p];
-    if (s.n_particle_bc > 0) {
-        const float time = (float)(*s.time);
-        const bool dirty = particle_bcs(s, s.perm[p], time, dt, mass, px, py, pz, vx, vy, vz);
+    if (!HOIST) late_loads();
+    if (s.n_particle_bc > 0 && any_particle_bc_active(s, time)) {
+        const bool dirty = particle_bcs(s, orig, time, dt, mass, px, py, pz, vx, vy, vz);
         // the reference stores the modified v; only particles outside the selection keep it (g2p overwrites the rest)
         if (dirty && live && !act) { f[(FS_V + 0) * cap + p] = vx; f[(FS_V + 1) * cap + p] = vy; f[(FS_V + 2) * cap + p] = vz; }
     }
-    const int material = s.material[p];
-    float mu = f[FS_MU * cap + p], lam = f[FS_LAM * cap + p];
-    const float vol = f[FS_VOL * cap + p];
     M3 tau;
     if (act) {
         M3 F;
@@ -320,14 +385,15 @@ mpm_fused_kernel(const FusedState s, const float dt) {
             C = Cn;
         }
     }
+    if (s.slab_step && act && (ax.b < s.base_lo || ax.b >= s.base_hi)) atomicExch(s.slab_err, 2);   // drifted beyond the slack planes
     // keep the grid kernel's node box ahead of the particles (rare: the box has a margin and is rebuilt at every sort)
     if (act && inside) {
-        if (ax.b < s.box[0]) atomicMin(s.box + 0, ax.b);
-        if (ay.b < s.box[1]) atomicMin(s.box + 1, ay.b);
-        if (az.b < s.box[2]) atomicMin(s.box + 2, az.b);
-        if (ax.b + 3 > s.box[3]) atomicMax(s.box + 3, ax.b + 3);
-        if (ay.b + 3 > s.box[4]) atomicMax(s.box + 4, ay.b + 3);
-        if (az.b + 3 > s.box[5]) atomicMax(s.box + 5, az.b + 3);
+        if (ax.b < box[0]) atomicMin(s.box + 0, ax.b);
+        if (ay.b < box[1]) atomicMin(s.box + 1, ay.b);
+        if (az.b < box[2]) atomicMin(s.box + 2, az.b);
+        if (ax.b + 3 > box[3]) atomicMax(s.box + 3, ax.b + 3);
+        if (ay.b + 3 > box[4]) atomicMax(s.box + 4, ay.b + 3);
+        if (az.b + 3 > box[5]) atomicMax(s.box + 5, az.b + 3);
     } else if (act) {
         atomicMin(s.box + 0, max(ax.b, 0)); atomicMin(s.box + 1, max(ay.b, 0)); atomicMin(s.box + 2, max(az.b, 0));
         atomicMax(s.box + 3, min(ax.b + 3, n)); atomicMax(s.box + 4, min(ay.b + 3, n)); atomicMax(s.box + 5, min(az.b + 3, n));
@@ -391,15 +457,102 @@ mpm_fused_kernel(const FusedState s, const float dt) {
                 a0 = segsum(a0); a1 = segsum(a1); a2 = segsum(a2); a3 = segsum(a3);
                 bool ok = head && contrib;
                 if (!inside) ok = ok && (unsigned)(ax.b + i) < (unsigned)n && (unsigned)(ay.b + j) < (unsigned)n && (unsigned)(az.b + k) < (unsigned)n;
-                if (ok) ptx::red_add_v4(gbase + 4 * (nbase + ((long long)i * n + j) * n + k), a0, a1, a2, a3);
+                ptx::red_add_v4_if(ok, gbase + 4 * (nbase + ((long long)i * n + j) * n + k), a0, a1, a2, a3);
             }
         }
 }
 
 // ------------------------------------------------------------------------------------------ grid update over the node box
+// ---- slab exchange block: lives at the start of the handle's exchange buffer, in front of grid_mv, so that ONE
+//      cudaIpc handle (or one pointer in single-process tests) gives a neighbour both the flags and the partial sums
+struct SlabFlags {
+    int scatter_done;     // substep whose scatter into grid_mv is complete and visible
+    int halo_done;        // substep whose overlap totals this rank has finished reading from its neighbours
+    int error;            // 1: a neighbour did not show up in time, 2: a particle drifted beyond the slack planes
+    int step;             // this rank's substep counter
+    int pad[60];
+};
+static_assert(sizeof(SlabFlags) == 256, "SlabFlags layout");
+
+__device__ __forceinline__ int ld_acquire_sys(const int* p) {
+    int v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(int* p, int v) {
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// Thread 0 of the block polls a neighbour's flag until it reaches `target` (bounded: ~1 s), then the block proceeds.
+__device__ __forceinline__ bool wait_peer_flag(const int* flag, int target, int* my_err) {
+    __shared__ int ok_s;
+    if (threadIdx.x == 0) {
+        int ok = 1;
+        if (flag) {
+            ok = 0;
+            for (long long it = 0; it < (1ll << 22); ++it) {
+                if (ld_acquire_sys(flag) >= target) { ok = 1; break; }
+                __nanosleep(200);
+            }
+            if (!ok) atomicExch(my_err, 1);
+        }
+        ok_s = ok;
+    }
+    __syncthreads();
+    const bool ok = ok_s != 0;
+    __syncthreads();
+    return ok;
+}
+
+struct HaloArgs {
+    SlabFlags* mine;
+    const SlabFlags* peer[2];       // left, right neighbour (nullptr at the domain ends)
+    const float4* peer_mv[2];
+    const float4* grid_mv;
+    float4* total[2];               // [ov planes][n][n]: own + neighbour partial sums on the planes shared with that neighbour
+    const int* box;
+    int n_grid;
+    int ov_lo[2], ov_hi[2];         // shared plane ranges [lo, hi)
+};
+
+// Overlap totals: total = own partial + neighbour's partial on the shared planes, inside this rank's node box (the only
+// nodes its particles read). Neither partial is modified here, so both neighbours compute the same sums (a + b == b + a).
+__global__ void __launch_bounds__(256)
+mpm_halo_kernel(const HaloArgs a) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");          // this rank's scatter of the substep is complete
+    const int k = a.mine->step;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { __threadfence_system(); st_release_sys(&a.mine->scatter_done, k); }
+    const int n = a.n_grid;
+    const int ly = a.box[1], lz = a.box[2], hy = a.box[4], hz = a.box[5];
+    const int ey = hy - ly, ez = hz - lz;
+#pragma unroll
+    for (int side = 0; side < 2; ++side) {
+        if (!a.peer[side]) continue;
+        if (!wait_peer_flag(&a.peer[side]->scatter_done, k, &a.mine->error)) return;
+        const int lx = max(a.ov_lo[side], a.box[0]), hx = min(a.ov_hi[side], a.box[3]);
+        const int ex = hx - lx;
+        if (ex <= 0 || ey <= 0 || ez <= 0) continue;
+        const long long total = (long long)ex * ey * ez;
+        for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+            const int iz = (int)(t % ez), iy = (int)((t / ez) % ey), ix = (int)(t / ((long long)ez * ey));
+            const size_t idx = ((size_t)(lx + ix) * n + (ly + iy)) * n + (lz + iz);
+            const float4 own = a.grid_mv[idx];
+            const float4 oth = a.peer_mv[side][idx];                 // peer memory (NVLink) or the other slab of a test
+            const size_t tix = ((size_t)(lx + ix - a.ov_lo[side]) * n + (ly + iy)) * n + (lz + iz);
+            a.total[side][tix] = make_float4(own.x + oth.x, own.y + oth.y, own.z + oth.z, own.w + oth.w);
+        }
+    }
+}
+
 struct GridBoxArgs {
     float4* grid_mv;
     float4* grid_v;
+    // slab mode (else mine == nullptr): planes [ov_lo, ov_hi) of side s take their {mv, m} from total[s]; the sweep waits
+    // until the neighbours have read this rank's partial sums of the substep before it clears them
+    SlabFlags* mine;
+    const SlabFlags* peer[2];
+    const float4* total[2];
+    int ov_lo[2], ov_hi[2];
     const int* box;              // lo.xyz, hi.xyz
     const double* time_in; double* time_out;
     const float* pts_in; float* pts_out;       // [n_bc][3] collider points, by parity (the cuboid ones move)
@@ -410,6 +563,14 @@ struct GridBoxArgs {
 
 __global__ void __launch_bounds__(256)
 mpm_gridbox_kernel(const GridBoxArgs s, const float dt, const double dt_d) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (s.mine) {
+        const int k = s.mine->step;
+        if (blockIdx.x == 0 && threadIdx.x == 0) { __threadfence_system(); st_release_sys(&s.mine->halo_done, k); }
+        for (int side = 0; side < 2; ++side)
+            if (s.peer[side] && !wait_peer_flag(&s.peer[side]->halo_done, k, &s.mine->error)) return;
+    }
     const int n = s.n_grid;
     const int lx = max(s.box[0], s.x_begin), ly = s.box[1], lz = s.box[2];
     const int hx = min(s.box[3], s.x_end), hy = s.box[4], hz = s.box[5];
@@ -437,7 +598,14 @@ mpm_gridbox_kernel(const GridBoxArgs s, const float dt, const double dt_d) {
         const int iz = (int)(t % ez), iy = (int)((t / ez) % ey), ix = (int)(t / ((long long)ez * ey));
         const int gx = lx + ix, gy = ly + iy, gz = lz + iz;
         const size_t idx = ((size_t)gx * n + gy) * n + gz;
-        const float4 mv = s.grid_mv[idx];
+        const float4 own = s.grid_mv[idx];
+        float4 mv = own;
+        if (s.mine) {
+#pragma unroll
+            for (int side = 0; side < 2; ++side)
+                if (s.peer[side] && gx >= s.ov_lo[side] && gx < s.ov_hi[side])
+                    mv = s.total[side][((size_t)(gx - s.ov_lo[side]) * n + gy) * n + gz];
+        }
         float vx = 0.f, vy = 0.f, vz = 0.f;
         if (mv.w > 1e-15f) {                                   // grid_normalization_and_gravity :398-409
             const float inv = 1.0f / mv.w;
@@ -487,7 +655,7 @@ mpm_gridbox_kernel(const GridBoxArgs s, const float dt, const double dt_d) {
             }
         }
         s.grid_v[idx] = make_float4(vx, vy, vz, 0.f);
-        if (mv.x != 0.f || mv.y != 0.f || mv.z != 0.f || mv.w != 0.f) s.grid_mv[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (own.x != 0.f || own.y != 0.f || own.z != 0.f || own.w != 0.f) s.grid_mv[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
 }
 

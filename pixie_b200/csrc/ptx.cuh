@@ -124,6 +124,49 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint6
         : "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// kind::f8f6f4 (8-bit float operands, K = 32 per instruction, fp32 accumulate): twice the MAC rate of kind::f16
+__device__ __forceinline__ void umma_f8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                        uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t"
+        "}\n"
+        :
+        : "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+template <bool kAccumulate>
+__device__ __forceinline__ void umma_f8_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc) {
+    if (kAccumulate) {
+        asm volatile(
+            "{\n\t"
+            ".reg .b64 da, db;\n\t"
+            ".reg .pred p;\n\t"
+            "mov.b64 da, {%1, %3};\n\t"
+            "mov.b64 db, {%2, %3};\n\t"
+            "setp.eq.b32 p, 0, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], da, db, %4, p;\n\t"
+            "}\n"
+            :
+            : "r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n\t"
+            ".reg .b64 da, db;\n\t"
+            ".reg .pred p;\n\t"
+            "mov.b64 da, {%1, %3};\n\t"
+            "mov.b64 db, {%2, %3};\n\t"
+            "setp.ne.b32 p, 0, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], da, db, %4, p;\n\t"
+            "}\n"
+            :
+            : "r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc)
+            : "memory");
+    }
+}
 // Same, with the two descriptors given as (low word, shared high word): only the 14-bit start address in the low
 // word differs between operands / K steps, so the issuing thread needs one 32-bit add per operand per MMA.
 template <bool kAccumulate>
@@ -205,6 +248,15 @@ __host__ __device__ __forceinline__ uint32_t make_idesc_f16(uint32_t M, uint32_t
            | ((M >> 4) << 24);  // M / 16
 }
 
+// kind::f8f6f4 instruction descriptor with A = B = E5M2, D = fp32, both operands K-major.
+__host__ __device__ __forceinline__ uint32_t make_idesc_e5m2(uint32_t M, uint32_t N) {
+    return (1u << 4)            // D format: F32
+           | (1u << 7)          // A format: E5M2 (E4M3 = 0)
+           | (1u << 10)         // B format: E5M2
+           | ((N >> 3) << 17)   // N / 8
+           | ((M >> 4) << 24);  // M / 16
+}
+
 // 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256): one full 32-byte sector per thread per instruction
 __device__ __forceinline__ void st_global_v8(float* p, const float* v) {
     asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]),
@@ -221,6 +273,18 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b),
                  "f"(c), "f"(d)
                  : "memory");
+}
+
+// Predicated form: no branch around the instruction (27 of these per particle sit in a fully unrolled loop; as
+// `if (ok) red` each cost a divergent branch — r02 ncu: branch_resolving was the top stall on that line)
+__device__ __forceinline__ void red_add_v4_if(bool ok, float* addr, float a, float b, float c, float d) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "@p red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n\t"
+        "}\n" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d), "r"((int)ok)
+        : "memory");
 }
 
 }  // namespace ptx

@@ -93,10 +93,11 @@ namespace {
 struct Builder {
     UNet& u;
     int NB;
-    bool precise;
+    bool precise;          // split-precision: every activation tensor carries a second tensor (`lo`)
+    bool f8corr;           // ... holding E5M2 correction operands (precision 2) instead of the fp16 residual (precision 1)
     std::string err;
 
-    explicit Builder(UNet& un) : u(un), NB(un.NBmax), precise(un.cfg.precision == 1) {}
+    explicit Builder(UNet& un) : u(un), NB(un.NBmax), precise(un.cfg.precision >= 1), f8corr(un.cfg.precision == 2) {}
 
     bool fail(const std::string& m) { if (err.empty()) err = m; return false; }
 
@@ -156,6 +157,7 @@ struct Builder {
         a.x = x.p; a.V = (int)vox(x.sp); a.C = x.C; a.stats = stats; a.mode = mode; a.groups = groups;
 
         a.gamma = gamma; a.beta = beta; a.eps = 1e-5f; a.act = act;
+        a.lo_mode = f8corr ? 1 : 0;
         if (dst) { a.dst = dst->hi; a.dst_lo = dst->lo; a.dst_ld = dst->C; a.dst_c0 = c0; }
         if (raw) { a.raw_dst = raw->hi; a.raw_lo = raw->lo; a.raw_ld = raw->C; a.raw_c0 = raw_c0; }
         UNet* up = &u;
@@ -189,7 +191,15 @@ struct Builder {
             d.segs.push_back({si, ks, 0});
             wptr.push_back(w->data.data()); cin_real.push_back(in.cin_real);
             u.flops += 2.0 * (double)vox(sp_out) * Cout * in.cin_real * kv;
-            if (precise && in.t.lo) {
+            if (f8corr && in.t.lo) {
+                // a_lo * w + a * w_lo in ONE segment of E5M2 operands at twice the fp16 MMA rate (2 pass-equivalents per
+                // algorithmic FLOP instead of 3; error 2^-3 of a single fp16 pass, measured 3e-4 max-abs end to end)
+                const int sl = (int)d.srcs.size();
+                d.srcs.push_back({in.t.lo, in.t.C, in.t.sp, in.t.sp, in.t.sp});
+                ConvDesc::Seg q{sl, ks, 0, 1};
+                d.segs.push_back(q);
+                wptr.push_back(w->data.data()); cin_real.push_back(in.cin_real);
+            } else if (precise && in.t.lo) {
                 // a_lo * w_hi  and  a_hi * w_lo
                 const int sl = (int)d.srcs.size();
                 d.srcs.push_back({in.t.lo, in.t.C, in.t.sp, in.t.sp, in.t.sp});
@@ -298,7 +308,8 @@ struct Builder {
         {
             UNet* upn = &u;
             const float* xp = x.p; __half* hi = up.hi; __half* lo = up.lo; const int sp = x.sp, C = x.C;
-            u.ops.push_back([=](cudaStream_t st) { return launch_upsample2(xp, hi, lo, upn->cur_nb, sp, C, st); });
+            const int lom = f8corr ? 1 : 0;
+            u.ops.push_back([=](cudaStream_t st) { return launch_upsample2(xp, hi, lo, lom, upn->cur_nb, sp, C, st); });
             u.op_kinds.push_back(PIXIE_OP_UPSAMPLE); u.op_flops.push_back(0);
         }
         DevT out = alloc_f32(x.C, 2 * x.sp, path);
@@ -320,7 +331,8 @@ struct Builder {
         {
             UNet* upn = &u;
             const float* qp = qkv.p; __half* hi = at.hi; __half* lo = at.lo;
-            u.ops.push_back([=](cudaStream_t s) { return launch_attention(qp, hi, lo, upn->cur_nb, T, C, s); });
+            const int lom = f8corr ? 1 : 0;
+            u.ops.push_back([=](cudaStream_t s) { return launch_attention(qp, hi, lo, lom, upn->cur_nb, T, C, s); });
             u.op_kinds.push_back(PIXIE_OP_ATTENTION); u.op_flops.push_back(0);
         }
         DevT out = alloc_f32(C, x.sp, path);
@@ -455,7 +467,7 @@ UNet* unet_create(const pixie_unet_config& cfg, std::string& err) {
     if (cfg.n_levels < 1 || cfg.n_levels > 8) { err = "n_levels out of range"; return nullptr; }
     if (cfg.grid_size % (1 << (cfg.n_levels - 1))) { err = "grid_size must be divisible by 2^(levels-1)"; return nullptr; }
     if (cfg.model_channels % 64) { err = "model_channels must be a multiple of 64"; return nullptr; }
-    if (cfg.precision != 0 && cfg.precision != 1) { err = "precision must be 0 or 1"; return nullptr; }
+    if (cfg.precision < 0 || cfg.precision > 2) { err = "precision must be 0 (fp16), 1 (fp16x3) or 2 (fp16 + e5m2 corrections)"; return nullptr; }
     auto* u = new UNet();
     u->cfg = cfg;
     u->use_graph = getenv("PIXIE_NO_GRAPH") == nullptr;

@@ -7,7 +7,10 @@
 #include "unet_kernels.cuh"
 
 #include <cuda_fp16.h>
+#include <cuda_fp8.h>
 #include <cstdint>
+
+#include "conv3d_igemm.cuh"   // kF8Shift
 
 namespace pixie {
 
@@ -19,12 +22,29 @@ __device__ __forceinline__ float act_apply(float v, int act) {
     return v;
 }
 
-// Packs 4 floats to fp16 (hi) and, when lo != nullptr, the rounding residual f - float(hi) to fp16.
-__device__ __forceinline__ void store_hi_lo(const float (&f)[4], __half* hi, __half* lo, size_t idx) {
+__device__ __forceinline__ uint32_t pack_e5m2x4(float a, float b, float c, float d) {
+    const uint32_t lo = __nv_cvt_float2_to_fp8x2(make_float2(a, b), __NV_SATFINITE, __NV_E5M2);
+    const uint32_t hi = __nv_cvt_float2_to_fp8x2(make_float2(c, d), __NV_SATFINITE, __NV_E5M2);
+    return lo | (hi << 16);
+}
+
+// Packs 4 floats (consecutive channels, idx % 4 == 0) to fp16 (hi) and, when lo != nullptr, what the split-precision
+// convolution needs next to it:
+//   lo_mode 0: the rounding residual f - float(hi) as fp16, same layout as hi;
+//   lo_mode 1: the E5M2 correction operands. `lo` is then a byte tensor with 2*ld bytes per voxel row; the 64-channel
+//              chunk k occupies bytes [128k, 128k+128): 64 x e5m2((f - float(hi)) * 2^kF8Shift) then 64 x e5m2(f * 2^-kF8Shift)
+//              (row strides and channel offsets are multiples of 64, so idx & 63 is the channel inside its chunk).
+__device__ __forceinline__ void store_hi_lo(const float (&f)[4], __half* hi, __half* lo, size_t idx, int lo_mode) {
     __half2 r0 = __floats2half2_rn(f[0], f[1]), r1 = __floats2half2_rn(f[2], f[3]);
     uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&r0); pk.y = *reinterpret_cast<uint32_t*>(&r1);
     *reinterpret_cast<uint2*>(hi + idx) = pk;
-    if (lo) {
+    if (lo && lo_mode == 1) {
+        const float2 b0 = __half22float2(r0), b1 = __half22float2(r1);
+        constexpr float up = (float)(1 << kF8Shift), down = 1.0f / (float)(1 << kF8Shift);
+        uint8_t* row = reinterpret_cast<uint8_t*>(lo) + 2 * (idx & ~(size_t)63) + (idx & 63);
+        *reinterpret_cast<uint32_t*>(row) = pack_e5m2x4((f[0] - b0.x) * up, (f[1] - b0.y) * up, (f[2] - b1.x) * up, (f[3] - b1.y) * up);
+        *reinterpret_cast<uint32_t*>(row + 64) = pack_e5m2x4(f[0] * down, f[1] * down, f[2] * down, f[3] * down);
+    } else if (lo) {
         const float2 b0 = __half22float2(r0), b1 = __half22float2(r1);
         __half2 l0 = __floats2half2_rn(f[0] - b0.x, f[1] - b0.y), l1 = __floats2half2_rn(f[2] - b1.x, f[3] - b1.y);
         uint2 pl; pl.x = *reinterpret_cast<uint32_t*>(&l0); pl.y = *reinterpret_cast<uint32_t*>(&l1);
@@ -139,7 +159,7 @@ norm_act_kernel(NormArgs a) {
             const int v = vb + u * rows_par;
             if (v >= v1) break;
             float f[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w};
-            if (a.raw_dst) store_hi_lo(f, a.raw_dst, a.raw_lo, ((size_t)nb * a.V + v) * a.raw_ld + a.raw_c0 + c);
+            if (a.raw_dst) store_hi_lo(f, a.raw_dst, a.raw_lo, ((size_t)nb * a.V + v) * a.raw_ld + a.raw_c0 + c, a.lo_mode);
             if (a.dst) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -148,7 +168,7 @@ norm_act_kernel(NormArgs a) {
                     else if (a.mode == kNormGN) y = (y - mean[j]) * rstd[j] * g[j] + b[j];
                     f[j] = act_apply(y, a.act);
                 }
-                store_hi_lo(f, a.dst, a.dst_lo, ((size_t)nb * a.V + v) * a.dst_ld + a.dst_c0 + c);
+                store_hi_lo(f, a.dst, a.dst_lo, ((size_t)nb * a.V + v) * a.dst_ld + a.dst_c0 + c, a.lo_mode);
             }
         }
     }
@@ -157,7 +177,7 @@ norm_act_kernel(NormArgs a) {
 // ------------------------------------------------------------------------------------ upsample x2
 // in: fp32 [NB][sp^3][C]; out: fp16 [NB][(2sp)^3][C], nearest neighbour.
 __global__ void __launch_bounds__(256)
-upsample2_kernel(const float* __restrict__ x, __half* __restrict__ y, __half* __restrict__ ylo, int sp, int C, long long total4) {
+upsample2_kernel(const float* __restrict__ x, __half* __restrict__ y, __half* __restrict__ ylo, int lo_mode, int sp, int C, long long total4) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total4) return;
     const int cols4 = C >> 2;
@@ -171,14 +191,14 @@ upsample2_kernel(const float* __restrict__ x, __half* __restrict__ y, __half* __
     const long long src = ((nb * sp + (d >> 1)) * sp + (h >> 1)) * sp + (w >> 1);
     const float4 a = __ldg(reinterpret_cast<const float4*>(x + src * C) + col);
     const float f[4] = {a.x, a.y, a.z, a.w};
-    store_hi_lo(f, y, ylo, (size_t)i * 4);
+    store_hi_lo(f, y, ylo, (size_t)i * 4, lo_mode);
 }
 
 // ------------------------------------------------------------------------------------ attention
 // qkv: fp32 [NB][T][3C] (q | k | v along channels, Conv1d output order, diffusion_network.py:233)
 // out: fp16 [NB][T][C] = softmax_s((q_t . k_s) / sqrt(C)) v_s.   One block per (query token, nb).
 __global__ void __launch_bounds__(256)
-attention_kernel(const float* __restrict__ qkv, __half* __restrict__ out, __half* __restrict__ out_lo, int T, int C) {
+attention_kernel(const float* __restrict__ qkv, __half* __restrict__ out, __half* __restrict__ out_lo, int lo_mode, int T, int C) {
     extern __shared__ float sm[];
     float* qs = sm;            // C
     float* sc = sm + C;        // T
@@ -225,7 +245,13 @@ attention_kernel(const float* __restrict__ qkv, __half* __restrict__ out, __half
         const float val = acc * inv;
         const __half hv = __float2half_rn(val);
         out[((size_t)nb * T + t) * C + c] = hv;
-        if (out_lo) out_lo[((size_t)nb * T + t) * C + c] = __float2half_rn(val - __half2float(hv));
+        const size_t idx = ((size_t)nb * T + t) * C + c;
+        if (out_lo && lo_mode == 1) {
+            constexpr float up = (float)(1 << kF8Shift), down = 1.0f / (float)(1 << kF8Shift);
+            uint8_t* row = reinterpret_cast<uint8_t*>(out_lo) + 2 * (idx & ~(size_t)63) + (idx & 63);
+            row[0] = (uint8_t)__nv_cvt_float_to_fp8((val - __half2float(hv)) * up, __NV_SATFINITE, __NV_E5M2);
+            row[64] = (uint8_t)__nv_cvt_float_to_fp8(val * down, __NV_SATFINITE, __NV_E5M2);
+        } else if (out_lo) out_lo[idx] = __float2half_rn(val - __half2float(hv));
     }
 }
 
@@ -295,17 +321,17 @@ int launch_norm_act(NormArgs a, int NB, cudaStream_t st) {
     return (int)cudaGetLastError();
 }
 
-int launch_upsample2(const float* x, __half* y, __half* ylo, int NB, int sp, int C, cudaStream_t st) {
+int launch_upsample2(const float* x, __half* y, __half* ylo, int lo_mode, int NB, int sp, int C, cudaStream_t st) {
     const long long total4 = (long long)NB * 8 * sp * sp * sp * (C / 4);
-    upsample2_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, st>>>(x, y, ylo, sp, C, total4);
+    upsample2_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, st>>>(x, y, ylo, lo_mode, sp, C, total4);
     return (int)cudaGetLastError();
 }
 
-int launch_attention(const float* qkv, __half* out, __half* out_lo, int NB, int T, int C, cudaStream_t st) {
+int launch_attention(const float* qkv, __half* out, __half* out_lo, int lo_mode, int NB, int T, int C, cudaStream_t st) {
     const size_t smem = (size_t)(C + T) * sizeof(float);
     if (smem > 48 * 1024) return 1;
     dim3 grid(T, NB);
-    attention_kernel<<<grid, 256, smem, st>>>(qkv, out, out_lo, T, C);
+    attention_kernel<<<grid, 256, smem, st>>>(qkv, out, out_lo, lo_mode, T, C);
     return (int)cudaGetLastError();
 }
 

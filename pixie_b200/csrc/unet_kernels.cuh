@@ -19,7 +19,9 @@ struct NormArgs {
     float eps = 1e-5f;
     int act = kActNone;
     __half* dst = nullptr;        // fp16 [NB][V][dst_ld], written at channel offset dst_c0 (may be null)
-    __half* dst_lo = nullptr;     // split-precision mode: fp16(y - float(fp16(y))), same layout as dst
+    __half* dst_lo = nullptr;     // split-precision modes: lo_mode 0 = fp16(y - float(fp16(y))), same layout as dst;
+                                  // lo_mode 1 = E5M2 correction operands (see store_hi_lo in unet_kernels.cu)
+    int lo_mode = 0;
     int dst_ld = 0, dst_c0 = 0;
     __half* raw_dst = nullptr;    // optional un-normalised fp16 copy of x
     __half* raw_lo = nullptr;
@@ -29,8 +31,8 @@ struct NormArgs {
 
 int launch_moments(const float* x, int NB, int V, int C, double* stats, cudaStream_t st);
 int launch_norm_act(NormArgs a, int NB, cudaStream_t st);
-int launch_upsample2(const float* x, __half* y, __half* ylo, int NB, int sp, int C, cudaStream_t st);
-int launch_attention(const float* qkv, __half* out, __half* out_lo, int NB, int T, int C, cudaStream_t st);
+int launch_upsample2(const float* x, __half* y, __half* ylo, int lo_mode, int NB, int sp, int C, cudaStream_t st);
+int launch_attention(const float* qkv, __half* out, __half* out_lo, int lo_mode, int NB, int T, int C, cudaStream_t st);
 int launch_pack_predictions(const float* seg, const float* cont, float* out, int NB, long long V, int n_classes, cudaStream_t st);
 int launch_ncdhw_to_ndhwc_f16(const float* x, __half* y, int NB, int C, int Cpad, long long V, cudaStream_t st);
 

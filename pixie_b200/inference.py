@@ -20,7 +20,7 @@ class MaterialFieldPredictor:
     def __init__(self, feature_channels: int, cond_dim: int = 32, model_channels: int = 64, num_res_blocks: int = 3,
                  channel_mult: Tuple[int, ...] = (1, 1, 2, 4), attention_resolutions: Tuple[int, ...] = (),
                  grid_size: int = 64, num_material_classes: int = 8, device="cuda:0", max_batch: int = 1,
-                 precision: str = "fp16x3"):
+                 precision: str = "fp16e5"):
         kw = dict(feature_channels=feature_channels, cond_dim=cond_dim, model_channels=model_channels,
                   num_res_blocks=num_res_blocks, channel_mult=channel_mult, attention_resolutions=attention_resolutions,
                   grid_size=grid_size, max_batch=max_batch, precision=precision)

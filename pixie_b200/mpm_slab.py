@@ -4,36 +4,44 @@ The reference runs one `MPM_Simulator_WARP` on "cuda:0" (mpm_solver_warp.py:47);
 shards ONE simulation along x: rank r owns grid planes [x0, x1) and the particles whose stencil base plane
 (`int(x/dx - 0.5)`, mpm_utils.py:344) lies there. One substep is
 
-    scatter   every rank scatters its particles into its own full-size {mv, m} grid         (pixie_mpm_substep_scatter)
-    exchange  neighbours swap the partial sums of the planes both of them touch and add      (NCCL send/recv, 4 planes/face)
-    finish    every rank normalises / applies the BCs on its owned + overlap planes and
-              gathers back to its particles                                                  (pixie_mpm_substep_finish)
+    scatter   every rank scatters its particles into its own full-size {mv, m} grid (g2p of the previous substep fused in)
+    halo      the partial sums of the planes two neighbours both touch are added: total = own + neighbour
+    finish    every rank normalises / applies the BCs on its owned + overlap planes
 
 and every `migrate_every` substeps particles whose base plane left [x0, x1) move to the neighbour (packed records over
 send/recv, live prefix of the bound arrays shrinks / grows). `slack` is how many planes a particle may drift outside
 its slab between two migrations; the overlap with the right neighbour is [x1 - slack, x1 + 2 + slack) because a particle
-touches planes base .. base+2. After the exchange both neighbours hold the COMPLETE sums on the overlap, so the grid
+touches planes base .. base+2. After the halo both neighbours hold the COMPLETE sums on the overlap, so the grid
 update there is computed redundantly and no second exchange is needed.
 
-Restrictions (checked): slabs must be at least 2 + 2*slack planes wide; boundary conditions that carry per-particle masks
-(impulses, velocity translation / rotation) are not migrated and are rejected.
+Two exchange mechanisms behind one orchestration:
+  * `FusedSlabBackend` (the product): the exchange runs ON THE DEVICE. Every handle exposes an exchange buffer
+    [flags][grid]; neighbours map each other's buffers (cudaIpc over NVLink between processes) and the halo kernel reads
+    the neighbour's partial sums directly, after a flag handshake; scatter -> halo -> finish chain in one CUDA graph, the
+    host only steps in for particle migration (NCCL send/recv of packed records).
+  * host exchange (`planes` / `planes_add`): what the CPU test double (tests/slab_backends.py) implements, so that the
+    orchestration — overlap ranges, migration, id bookkeeping — is exercised without a GPU, in one process and over gloo.
 
-The orchestration is backend-agnostic: `CudaSlabBackend` drives the C ABI; the CPU tests drive the same orchestration
-with a CPU test double (tests/slab_backends.py), in one process and over gloo.
+Restrictions (checked): slabs must be at least 2 + 2*slack planes wide; a particle that drifts more than `slack` planes
+out of its slab between two migrations raises (migrate more often); boundary conditions that carry per-particle masks
+(impulses, velocity translation / rotation) are not migrated and are rejected.
 """
 from __future__ import annotations
 
 import ctypes as C
 from typing import List, Optional, Sequence, Tuple
 
+import numpy as np
 import torch
 
 from . import _lib
 
 
 # ------------------------------------------------------------------------------------------- backends
-class CudaSlabBackend:
-    """One rank's solver: a `MPM_Simulator_WARP` shim created with `capacity` particles of which a prefix is live."""
+class FusedSlabBackend:
+    """One rank's solver (a `MPM_Simulator_WARP` shim created with `capacity` particles of which a prefix is live) on the
+    default path, overlap exchange on the device."""
+    device_exchange = True
 
     #: per-particle fields that migrate with a particle: (C-ABI field name, width)
     FIELDS = [("X", 3), ("V", 3), ("F", 9), ("F_TRIAL", 9), ("C", 9), ("STRESS", 9), ("R", 9), ("COV", 6), ("INIT_COV", 6),
@@ -49,12 +57,11 @@ class CudaSlabBackend:
         self.inv_dx = float(solver.mpm_model.inv_dx)
         if solver._masks:
             raise ValueError("slab-decomposed runs do not migrate per-particle BC masks (impulses, velocity modifiers)")
-        n = self.n_grid
-        with torch.cuda.device(self.device):
-            self.grid = torch.zeros((n, n * n * 4), dtype=torch.float32, device=self.device)
-        self._check(self.lib.pixie_mpm_bind_grid(solver._handle, C.c_void_p(self.grid.data_ptr())))
+        base, nbytes = C.c_void_p(), C.c_size_t()
+        self._check(self.lib.pixie_mpm_exchange_buffer(solver._handle, C.byref(base), C.byref(nbytes)))
+        self.xbuf, self.xbuf_bytes = base.value, nbytes.value
+        self._opened = []
         self._active = -1
-        self._slab = None
         self.set_active(n_active)
 
     def _check(self, rc: int):
@@ -64,28 +71,56 @@ class CudaSlabBackend:
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
-    # -- substep halves
-    def scatter(self, dt: float):
+    # -- exchange set-up
+    def export_handle(self) -> bytes:
+        """64-byte cudaIpc handle of the exchange buffer, for a neighbour in another process."""
+        buf = C.create_string_buffer(64)
         with torch.cuda.device(self.device):
-            self._check(self.lib.pixie_mpm_substep_scatter(self.solver._handle, float(dt), self._stream()))
+            self._check(self.lib.pixie_ipc_export(C.c_void_p(self.xbuf), buf))
+        return buf.raw
+
+    def open_handle(self, handle: bytes) -> int:
+        p = C.c_void_p()
+        with torch.cuda.device(self.device):
+            self._check(self.lib.pixie_ipc_open(C.create_string_buffer(handle, 64), C.byref(p)))
+        self._opened.append(p.value)
+        return p.value
+
+    def attach(self, x0: int, x1: int, slack: int, left: Optional[int], right: Optional[int]):
+        """Neighbours' exchange buffers as device pointers valid in this process (None at the domain ends)."""
+        with torch.cuda.device(self.device):
+            self._check(self.lib.pixie_mpm_slab_attach(self.solver._handle, int(x0), int(x1), int(slack),
+                                                       C.c_void_p(left) if left else None, C.c_void_p(right) if right else None))
+
+    def close(self):
+        for p in self._opened:
+            self.lib.pixie_ipc_close(C.c_void_p(p))
+        self._opened = []
+
+    # -- substep phases (each only enqueues kernels)
+    def _phase(self, ph: int, dt: float):
+        with torch.cuda.device(self.device):
+            self._check(self.lib.pixie_mpm_slab_phase(self.solver._handle, ph, float(dt), self._stream()))
+
+    def scatter(self, dt: float):
+        self._phase(0, dt)
+
+    def halo(self, dt: float):
+        self._phase(1, dt)
 
     def finish(self, dt: float, lo: int, hi: int):
+        self._phase(2, dt)
+
+    def step(self, n: int, dt: float):
+        """`n` whole substeps (scatter, halo, finish chained on the device, replayed from a CUDA graph)."""
+        self.solver.p2g2p_n(n, dt)
+
+    def error(self) -> int:
+        flag = C.c_int(0)
         with torch.cuda.device(self.device):
-            if (lo, hi) != self._slab:
-                self._check(self.lib.pixie_mpm_set_slab(self.solver._handle, int(lo), int(hi)))
-                self._slab = (lo, hi)
-            self._check(self.lib.pixie_mpm_substep_finish(self.solver._handle, float(dt), self._stream()))
-
-    # -- grid planes {mv.xyz, m}
-    def planes(self, a: int, b: int) -> torch.Tensor:
-        return self.grid[a:b].clone()
-
-    def planes_view(self, a: int, b: int) -> torch.Tensor:
-        """No copy: x is the slowest grid dimension, so a plane range is one contiguous block (valid until the next add)."""
-        return self.grid[a:b]
-
-    def planes_add(self, a: int, b: int, t: torch.Tensor):
-        self.grid[a:b] += t.to(self.grid.dtype)
+            torch.cuda.current_stream(self.device).synchronize()
+            self._check(self.lib.pixie_mpm_slab_error(self.solver._handle, C.byref(flag)))
+        return flag.value
 
     # -- particles
     @property
@@ -100,19 +135,12 @@ class CudaSlabBackend:
             self._active = int(n)
 
     def get(self, name: str) -> torch.Tensor:
-        t = self.solver._t[name]
+        t = self.solver._t[name]           # syncs: results of the substeps so far are written back first
         return t.view(self.capacity, t.numel() // self.capacity)[: self._active]
 
-    def records(self) -> torch.Tensor:
-        """[n_active, W] float32; integer fields are bit-cast, not converted."""
-        cols = []
-        for name, w in self.FIELDS:
-            t = self.get(name)
-            cols.append(t.view(torch.float32) if t.dtype == torch.int32 else t)
-        return torch.cat(cols, dim=1)
-
     def records_at(self, index: torch.Tensor) -> torch.Tensor:
-        """Records of the particles `index` only (migration touches a few thousand of them, not the whole slab)."""
+        """Records of the particles `index` only (migration touches a few thousand of them, not the whole slab);
+        [len(index), W] float32, integer fields bit-cast, not converted."""
         cols = []
         for name, w in self.FIELDS:
             t = self.get(name)[index]
@@ -137,29 +165,37 @@ class CudaSlabBackend:
             c += w
         self.set_active(n_keep + n_new)
 
-    def set_records(self, rec: torch.Tensor):
-        n = rec.shape[0]
-        self.set_active(n)
-        c = 0
-        for name, w in self.FIELDS:
-            dst = self.solver._t[name].view(self.capacity, w)
-            src = rec[:, c:c + w].contiguous()
-            dst[:n] = src.view(torch.int32) if dst.dtype == torch.int32 else src
-            c += w
-
 
 # ------------------------------------------------------------------------------------------- orchestration
 def slab_bounds(n_grid: int, world: int, rank: int) -> Tuple[int, int]:
     return rank * n_grid // world, (rank + 1) * n_grid // world
 
 
+def balanced_slab_bounds(base_planes, n_grid: int, world: int, min_width: int) -> List[Tuple[int, int]]:
+    """Plane ranges with (nearly) equal particle counts: cuts at the quantiles of the particles' stencil base planes, every
+    slab at least `min_width` planes wide (>= 2 + 2*slack). Equal-width slabs leave most ranks idle when the particles
+    occupy a fraction of the domain (BASELINE config 5: a 0.4-wide block in a 256^3 grid = 3 of 8 slabs)."""
+    base = np.sort(np.asarray(base_planes).astype(np.int64))
+    if world * min_width > n_grid:
+        raise ValueError("domain too small for this many slabs")
+    cuts = [0]
+    for r in range(1, world):
+        q = int(base[min(len(base) - 1, (len(base) * r) // world)]) if len(base) else r * n_grid // world
+        lo = cuts[-1] + min_width                      # keep the previous slab wide enough ...
+        hi = n_grid - (world - r) * min_width          # ... and room for the remaining ones
+        cuts.append(max(lo, min(q, hi)))
+    cuts.append(n_grid)
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
 class SlabRank:
     """Phase methods of one rank; a driver (`DistSlabDriver` or `LocalSlabCluster`) sequences them."""
 
-    def __init__(self, backend, rank: int, world: int, slack: int = 1, migrate_every: int = 8, ids: Optional[torch.Tensor] = None):
+    def __init__(self, backend, rank: int, world: int, slack: int = 1, migrate_every: int = 8, ids: Optional[torch.Tensor] = None,
+                 bounds: Optional[Tuple[int, int]] = None):
         self.b, self.rank, self.world, self.slack, self.migrate_every = backend, rank, world, slack, migrate_every
         n = backend.n_grid
-        self.x0, self.x1 = slab_bounds(n, world, rank)
+        self.x0, self.x1 = bounds if bounds is not None else slab_bounds(n, world, rank)
         if world > 1 and (self.x1 - self.x0) < 2 + 2 * slack:
             raise ValueError(f"slab [{self.x0}, {self.x1}) is narrower than 2 + 2*slack = {2 + 2 * slack} planes")
         self.has_left, self.has_right = rank > 0, rank < world - 1
@@ -204,11 +240,28 @@ class SlabRank:
         return self.world > 1 and self.steps % self.migrate_every == 0
 
     # -- migration phases
+    def check_device_error(self):
+        """Device-exchange backends: raises if a neighbour never showed up or a particle out-ran the slack planes."""
+        err = self.b.error() if hasattr(self.b, "error") else 0
+        if err == 1:
+            raise RuntimeError(f"slab rank {self.rank}: a neighbour did not reach the exchange (flag timeout)")
+        if err == 2:
+            raise RuntimeError(f"slab rank {self.rank}: a particle drifted more than slack={self.slack} planes out of "
+                               f"[{self.x0}, {self.x1}) between two migrations; lower migrate_every or raise slack")
+
     def migrate_collect(self):
         """Splits the live particles into stay / to_left / to_right. Returns (stay_index, (rec, ids) left, (rec, ids) right)."""
+        self.check_device_error()
         x = self.b.get("X")[:, 0]
         # base plane exactly as the kernels compute it: float32 product, truncation toward zero (mpm_utils.py:344-346)
         base = (x.to(torch.float32) * torch.tensor(self.b.inv_dx, dtype=torch.float32, device=x.device) - 0.5).to(torch.int32)
+        # a particle further out than the slack planes has scattered into planes nobody exchanged or swept: its slab's
+        # result is already wrong, so fail loudly instead of migrating it
+        lo_ok = self.x0 - self.slack if self.has_left else -(1 << 30)
+        hi_ok = self.x1 + self.slack if self.has_right else (1 << 30)
+        if base.numel() and (int(base.min()) < lo_ok or int(base.max()) >= hi_ok):
+            raise RuntimeError(f"slab rank {self.rank}: a particle drifted more than slack={self.slack} planes out of "
+                               f"[{self.x0}, {self.x1}) between two migrations; lower migrate_every or raise slack")
         go_left = (base < self.x0) if self.has_left else torch.zeros_like(base, dtype=torch.bool)
         go_right = (base >= self.x1) if self.has_right else torch.zeros_like(base, dtype=torch.bool)
         stay_idx = torch.nonzero(~(go_left | go_right)).flatten()
@@ -219,6 +272,7 @@ class SlabRank:
         else:
             rec = self.b.records()
             pack = lambda i: (rec[i], ids[i])
+        # a mover more than one slab away cannot be handed to a direct neighbour
         return stay_idx, pack(il), pack(ir)
 
     def migrate_apply(self, stay_idx, from_left, from_right):
@@ -238,16 +292,27 @@ class LocalSlabCluster:
 
     def __init__(self, ranks: Sequence[SlabRank]):
         self.ranks = list(ranks)
+        self.device_exchange = bool(getattr(self.ranks[0].b, "device_exchange", False))
+        if self.device_exchange:
+            # same process: the neighbours' exchange buffers are plain device pointers; the phases of all slabs are
+            # enqueued on one stream in order, so every flag a kernel waits for has already been raised
+            for i, r in enumerate(self.ranks):
+                r.b.attach(r.x0, r.x1, r.slack, self.ranks[i - 1].b.xbuf if r.has_left else None,
+                           self.ranks[i + 1].b.xbuf if r.has_right else None)
 
     def substep(self, dt: float):
         R = self.ranks
         for r in R:
             r.scatter(dt)
-        snaps = [r.snapshot() for r in R]
-        for i, r in enumerate(R):
-            from_left = snaps[i - 1][1] if r.has_left else None       # left neighbour's right overlap = my left overlap
-            from_right = snaps[i + 1][0] if r.has_right else None
-            r.accumulate(from_left, from_right)
+        if self.device_exchange:
+            for r in R:
+                r.b.halo(dt)
+        else:
+            snaps = [r.snapshot() for r in R]
+            for i, r in enumerate(R):
+                from_left = snaps[i - 1][1] if r.has_left else None       # left neighbour's right overlap = my left overlap
+                from_right = snaps[i + 1][0] if r.has_right else None
+                r.accumulate(from_left, from_right)
         for r in R:
             r.finish(dt)
         if R[0].due_for_migration():
@@ -273,6 +338,39 @@ class DistSlabDriver:
         import torch.distributed as dist
         self.r, self.dist, self.group = rank_obj, dist, group
         self._recv = None
+        self.device_exchange = bool(getattr(rank_obj.b, "device_exchange", False))
+        if self.device_exchange:
+            # every rank publishes the cudaIpc handle of its exchange buffer; each maps its two neighbours' buffers
+            r = rank_obj
+            handles = [None] * r.world
+            dist.all_gather_object(handles, r.b.export_handle(), group=group)
+            left = r.b.open_handle(handles[r.rank - 1]) if r.has_left else None
+            right = r.b.open_handle(handles[r.rank + 1]) if r.has_right else None
+            r.b.attach(r.x0, r.x1, r.slack, left, right)
+            dist.barrier(group=group)                    # nobody starts stepping before every buffer is mapped
+
+    def run(self, n_substeps: int, dt: float):
+        """`n_substeps` substeps; between migrations the device runs on its own (graph replays), the host only steps in every
+        `migrate_every` substeps. Falls back to substep() for host-exchange backends."""
+        r = self.r
+        if not self.device_exchange:
+            for _ in range(n_substeps):
+                self.substep(dt)
+            return
+        done = 0
+        while done < n_substeps:
+            chunk = min(n_substeps - done, r.migrate_every - (r.steps % r.migrate_every))
+            r.b.step(chunk, dt)
+            r.steps += chunk
+            done += chunk
+            if r.due_for_migration():
+                self._migrate()
+
+    def _migrate(self):
+        r = self.r
+        stay, go_left, go_right = r.migrate_collect()
+        from_left, from_right = self._swap_var(go_left if r.has_left else None, go_right if r.has_right else None)
+        r.migrate_apply(stay, from_left, from_right)
 
     def _swap(self, to_left: Optional[torch.Tensor], to_right: Optional[torch.Tensor], like_left=None, like_right=None, reuse=False):
         """Symmetric neighbour exchange. `like_*` give the shape of what is received (default: what is sent); with
@@ -307,6 +405,11 @@ class DistSlabDriver:
 
     def substep(self, dt: float):
         r = self.r
+        if self.device_exchange:
+            r.b.scatter(dt); r.b.halo(dt); r.finish(dt)
+            if r.due_for_migration():
+                self._migrate()
+            return
         r.scatter(dt)
         left, right = r.snapshot_views()
         if self._recv is None:          # overlap-plane receive buffers, allocated once

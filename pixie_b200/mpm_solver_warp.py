@@ -327,6 +327,10 @@ class MPM_Simulator_WARP:
         """`n_substeps` x p2g2p without returning to Python (CUDA-graph replay)."""
         _lib.check(_lib.load().pixie_mpm_step(self._handle, int(n_substeps), float(dt), self._stream()))
 
+    def launch_count(self) -> int:
+        """Kernels of libpixie_b200 launched for this solver so far (graph replays count their nodes)."""
+        return int(_lib.load().pixie_mpm_launch_count(self._handle))
+
     def reset_densities_and_update_masses(self, all_particle_densities, device="cuda:0"):
         d = all_particle_densities.clone().detach().to(self._device, torch.float32).contiguous()
         self._bind("DENSITY", d)

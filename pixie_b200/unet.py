@@ -18,6 +18,10 @@ import torch
 
 from . import _lib
 
+#: numerics of the convolutions (pixie_unet_config.precision): one fp16 tensor-core pass; three fp16 passes on hi/lo split
+#: operands; or one fp16 pass + one E5M2 pass carrying the first-order rounding terms (2 pass-equivalents, meets 1e-3)
+PRECISIONS = {"fp16": 0, "fp16x3": 1, "fp16e5": 2}
+
 
 def _expected_keys(feature_channels, cond_dim, model_channels, num_res_blocks, channel_mult, grid_size, out_channels):
     """State-dict keys and shapes of the reference module, derived from the
@@ -94,8 +98,8 @@ class _B200UNet:
             raise NotImplementedError(
                 "attention_resolutions must be () (config/training/default.yaml:96); the bottleneck "
                 "AttentionBlock of middle_block is always built")
-        if precision not in ("fp16", "fp16x3"):
-            raise ValueError("precision must be 'fp16' or 'fp16x3'")
+        if precision not in PRECISIONS:
+            raise ValueError("precision must be one of " + ", ".join(repr(k) for k in PRECISIONS))
         self.feature_channels, self.cond_dim = int(feature_channels), int(cond_dim)
         self.model_channels, self.num_res_blocks = int(model_channels), int(num_res_blocks)
         self.channel_mult = tuple(int(m) for m in channel_mult)
@@ -170,7 +174,7 @@ class _B200UNet:
             cfg.channel_mult[i] = m
         cfg.grid_size, cfg.out_channels = self.grid_size, self.out_channels
         cfg.max_batch = self.max_batch
-        cfg.precision = 1 if self.precision == "fp16x3" else 0
+        cfg.precision = PRECISIONS[self.precision]
         h = C.c_void_p()
         dev = self._device or torch.device("cuda", torch.cuda.current_device())
         with torch.cuda.device(dev):

@@ -42,12 +42,25 @@ def time_it(tag, steps, **kw):
 
 if __name__ == "__main__":
     steps = int(sys.argv[1]) if len(sys.argv) > 1 else 1000
-    for agg in (3, 2, 1, 0):
+    mode = sys.argv[2] if len(sys.argv) > 2 else "full"
+    if mode == "ab":          # same-box A/B of the launch / load-placement variants (each process-wide switch is read once per process)
+        import subprocess
+        for hoist in ("0", "1"):
+            for pdl in ("1", "0"):
+                env = dict(os.environ, PIXIE_MPM_HOIST=hoist, PIXIE_MPM_PDL=pdl)
+                out = subprocess.run([sys.executable, __file__, str(steps), "one"], env=env, capture_output=True, text=True).stdout
+                print(f"hoist={hoist} pdl={pdl}: " + " | ".join(l for l in out.splitlines() if "us/substep" in l), flush=True)
+        sys.exit(0)
+    if mode == "one":
+        time_it("fused", steps)
+        sys.exit(0)
+    for agg in ((2, 3, 1) if mode == "full" else (2,)):
         os.environ["PIXIE_MPM_AGG"] = str(agg)
         time_it(f"fused agg={agg}", steps)
-    os.environ["PIXIE_MPM_AGG"] = "3"
+    os.environ["PIXIE_MPM_AGG"] = "2"
     time_it("fused, no BCs", steps, bcs=False)
-    time_it("fused, sand", steps, materials=(2,))
-    time_it("fused, 1M / 128^3", 200, n=1_000_000, ng=128)
-    os.environ["PIXIE_MPM_DIRECT"] = "1"
-    time_it("direct (r01 kernels)", steps)
+    if mode == "full":
+        time_it("fused, sand", steps, materials=(2,))
+        time_it("fused, 1M / 128^3", 200, n=1_000_000, ng=128)
+        os.environ["PIXIE_MPM_DIRECT"] = "1"
+        time_it("direct (r01 kernels)", steps)

@@ -156,3 +156,22 @@ def test_drift_vs_fp64_oracle(built_lib, cuda_dev, direct):
     drift = _err(s, o64, "X")
     floor = np.abs(o32.get("X") - o64.get("X")).max()
     assert drift < 1e-4 and drift < 20 * floor + 1e-6
+
+
+def test_north_star_drift_100k_particles_1000_substeps(built_lib, cuda_dev):
+    """BASELINE.json north star: "particle-position drift < 1e-4 vs the reference over 1000 steps" at the benchmarked size
+    (100k particles, 64^3 grid; the reference's own loop is gs_simulation.py:633-634). The reference's
+    arithmetic is fp32, so its own run-to-run / reordering noise is reported next to the drift: fp32 oracle vs fp64 oracle."""
+    s, o64, _ = _pair(100_000, 64, (0,), seed=0, prec="f64", moving=False)
+    _, o32, _ = _pair(100_000, 64, (0,), seed=0, prec="f32", moving=False)
+    for o in (o64, o32):
+        o.set_params(parallel_p2g=1)            # OpenMP scatter (atomics): the serial one would take minutes here
+    s.p2g2p_n(1000, 1e-4)
+    o64.step(1000, 1e-4); o32.step(1000, 1e-4)
+    torch.cuda.synchronize()
+    drift = _err(s, o64, "X")
+    floor = np.abs(o32.get("X") - o64.get("X")).max()
+    print(f"drift vs fp64 oracle {drift:.3e}; fp32 oracle vs fp64 oracle {floor:.3e}; vs fp32 oracle {_err(s, o32, 'X'):.3e}")
+    assert abs(s.time - 0.1) < 1e-9
+    assert drift < 1e-4
+    assert drift < 20 * floor + 1e-6

@@ -3,6 +3,8 @@ the C ABI (pixie_b200/_lib.py -> libpixie_b200.so); the oracle is only the check
 
 Tolerances (max-abs on outputs of magnitude ~3):
   fp16x3  : < 1e-3   — the north-star material-field tolerance (measured ~5e-5)
+  fp16e5  : < 1e-3   — one fp16 pass + one E5M2 pass carrying a_lo*w + a*w_lo (2 pass-equivalents; predicted 3e-4 by a CPU
+                       emulation of the rounding points, see DESIGN.md "Numerics") — the default mode of bench.py
   fp16    : < 2e-2   — one tensor-core pass with fp16 operands has a 2^-11 relative rounding per operand,
                        the same mantissa as the TF32 arithmetic the reference's own GPU run uses
                        (torch default cudnn.allow_tf32); measured ~5e-3 ("Numerics").
@@ -18,7 +20,7 @@ from oracle import unet_ref as O
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-TOL = {"fp16x3": 1e-3, "fp16": 2e-2}
+TOL = {"fp16x3": 1e-3, "fp16e5": 1e-3, "fp16": 2e-2}
 
 
 def _mine(cls_name, C, G, out, precision, sd, max_batch=2, cfg=None):
@@ -39,7 +41,7 @@ def test_conv_bringup_binary(built_lib, cuda_dev):
     assert "fail=0" in r.stdout, r.stdout[-3000:]
 
 
-@pytest.mark.parametrize("precision", ["fp16x3", "fp16"])
+@pytest.mark.parametrize("precision", ["fp16e5", "fp16x3", "fp16"])
 def test_golden_vectors(built_lib, cuda_dev, precision):
     """Outputs of the REFERENCE modules (tests/golden/make_unet_golden.py) on seeded inputs."""
     g = np.load(os.path.join(ROOT, "tests", "golden", "unet_small.npz"))
@@ -53,7 +55,7 @@ def test_golden_vectors(built_lib, cuda_dev, precision):
         assert np.abs(y - g[f"{name}_y"]).max() < TOL[precision]
 
 
-@pytest.mark.parametrize("precision", ["fp16x3", "fp16"])
+@pytest.mark.parametrize("precision", ["fp16e5", "fp16x3", "fp16"])
 @pytest.mark.parametrize("C,G", [(128, 16), (512, 32)])
 def test_parity_vs_oracle_both_networks(built_lib, cuda_dev, precision, C, G):
     """BASELINE config 1 (32^3 x 512) and a smaller grid; segmentation argmax must agree wherever the
@@ -209,21 +211,22 @@ def test_full_size_64_cubed_512(built_lib, cuda_dev):
     x16 = (torch.randn(1, G, G, G, C, generator=torch.Generator().manual_seed(1)) * 0.05).to(torch.float16)
     with torch.no_grad():
         y_ref = reg(x16.float().permute(0, 4, 1, 2, 3).contiguous())
-    for precision in ("fp16x3", "fp16"):
+    for precision in ("fp16e5", "fp16x3", "fp16"):
         net = _mine("RegressionUNet", C, G, 3, precision, reg.state_dict(), max_batch=1)
         y = net.forward_channels_last_f16(x16.cuda())
         y2 = net.forward_channels_last_f16(x16.cuda())
         net.check()
         assert (y - y2).abs().max() < (1e-4 if precision == "fp16x3" else TOL[precision])
+        print(f"64^3x512 {precision}: max-abs vs fp32 oracle {float((y.cpu() - y_ref).abs().max()):.3e}")
         assert (y.cpu() - y_ref).abs().max() < TOL[precision]
         del net
         torch.cuda.empty_cache()
     with torch.no_grad():
         ys = seg(x16.float().permute(0, 4, 1, 2, 3).contiguous())
-    net = _mine("SegmentationUNet", C, G, 8, "fp16x3", seg.state_dict(), max_batch=1)
+    net = _mine("SegmentationUNet", C, G, 8, "fp16e5", seg.state_dict(), max_batch=1)
     zs = net.forward_channels_last_f16(x16.cuda()).cpu()
     net.check()
-    assert (zs - ys).abs().max() < TOL["fp16x3"]
+    assert (zs - ys).abs().max() < TOL["fp16e5"]
     top2 = ys.topk(2, dim=1).values
-    confident = (top2[:, 0] - top2[:, 1]) > 10 * TOL["fp16x3"]
+    confident = (top2[:, 0] - top2[:, 1]) > 10 * TOL["fp16e5"]
     assert (zs.argmax(1) == ys.argmax(1))[confident].all()

@@ -140,16 +140,11 @@ def _cuda_solver(fields, idx, capacity):
     return s
 
 
-@pytest.mark.gpu
-def test_cuda_slabs_match_single_domain_cuda():
-    """Two CUDA solvers (one per slab) on one device, hand-over exchange: same trajectory as the undivided CUDA run."""
+def _cuda_cluster(fields, world, migrate_every, bounds=None):
     import ctypes as C
     from pixie_b200 import _lib
-    from pixie_b200.mpm_slab import CudaSlabBackend
-    from slab_backends import make_scene
+    from pixie_b200.mpm_slab import FusedSlabBackend
     lib = _lib.require_device()
-    fields = make_scene(N, G, LIM)
-    steps = 60
 
     def finish_setup(s):
         st = s._stream()
@@ -157,23 +152,44 @@ def test_cuda_slabs_match_single_domain_cuda():
         _lib.check(lib.pixie_mpm_compute_mu_lam(s._handle, st))
         s.add_bounding_box()
 
+    ranks = []
+    for r in range(world):
+        if bounds is None:
+            idx = _owned(fields, world, r)
+        else:
+            base = (fields["X"][:, 0].astype(np.float32) * np.float32(G / LIM) - np.float32(0.5)).astype(np.int32)
+            lo = -10 ** 9 if r == 0 else bounds[r][0]
+            hi = 10 ** 9 if r == world - 1 else bounds[r][1]
+            idx = np.where((base >= lo) & (base < hi))[0]
+        s = _cuda_solver(fields, idx, N)
+        finish_setup(s)
+        ranks.append(SlabRank(FusedSlabBackend(s, len(idx)), r, world, slack=1, migrate_every=migrate_every,
+                              ids=torch.from_numpy(idx.astype(np.int64)), bounds=None if bounds is None else bounds[r]))
+    return ranks, finish_setup
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world,migrate_every", [(2, 4), (3, 2), (4, 3)])
+def test_cuda_slabs_match_single_domain_cuda(world, migrate_every):
+    """`world` CUDA solvers (one per slab) on one device, overlap totals read by the halo kernel from the neighbours' exchange
+    buffers (plain pointers inside one process): same trajectory as the undivided CUDA run and as the f64 oracle."""
+    from slab_backends import make_scene
+    fields = make_scene(N, G, LIM)
+    steps = 60
+    ranks, finish_setup = _cuda_cluster(fields, world, migrate_every,
+                                        bounds=None if world < 4 else [(0, 5), (5, 9), (9, 13), (13, 16)])
     whole = _cuda_solver(fields, np.arange(N), N)
     finish_setup(whole)
     whole.p2g2p_n(steps, DT)
     x_whole = whole._t["X"].view(N, 3).cpu().numpy().astype(np.float64)
 
-    world = 2
-    ranks = []
-    for r in range(world):
-        idx = _owned(fields, world, r)
-        s = _cuda_solver(fields, idx, N)
-        finish_setup(s)
-        ranks.append(SlabRank(CudaSlabBackend(s, len(idx)), r, world, slack=1, migrate_every=4, ids=torch.from_numpy(idx.astype(np.int64))))
     before = [r.b.active for r in ranks]
     cl = LocalSlabCluster(ranks)
     for _ in range(steps):
         cl.substep(DT)
     torch.cuda.synchronize()
+    for r in ranks:
+        r.check_device_error()
     assert sum(r.b.active for r in ranks) == N and [r.b.active for r in ranks] != before
     x_slab = cl.gather("X").numpy().reshape(N, 3)
     ref = _reference(fields, steps)
@@ -181,3 +197,21 @@ def test_cuda_slabs_match_single_domain_cuda():
     # fp32 atomics: both CUDA runs sit within the same distance of the f64 oracle, and of each other
     assert np.abs(x_slab - x_whole).max() < 2e-5
     assert np.abs(x_slab - x_ref).max() < 5e-5
+    ft = cl.gather("F_TRIAL").numpy().reshape(N, 9)
+    assert np.abs(ft - np.asarray(ref.get("F_TRIAL")).reshape(N, 9)).max() < 5e-4
+
+
+@pytest.mark.gpu
+def test_cuda_slab_drift_beyond_slack_is_reported():
+    """A particle that out-runs the slack planes between two migrations must raise instead of silently corrupting the grid."""
+    from slab_backends import make_scene
+    fields = make_scene(N, G, LIM)
+    fields["V"][:, 0] = 12.0                                  # 12 * 2e-3 * 16 = 0.38 cells per substep, 20 substeps without migration
+    ranks, _ = _cuda_cluster(fields, 2, migrate_every=1000)
+    cl = LocalSlabCluster(ranks)
+    with pytest.raises(RuntimeError, match="drifted more than slack"):
+        for _ in range(20):
+            cl.substep(DT)
+        torch.cuda.synchronize()
+        for r in ranks:
+            r.check_device_error()
