@@ -776,6 +776,12 @@ static FusedState fused_state(Mpm* m) {
     t.rpic_damping = q.rpic_damping; t.alpha = q.alpha; t.hardening = q.hardening; t.xi = q.xi;
     t.plastic_viscosity = q.plastic_viscosity; t.softening = q.softening;
     t.update_cov_with_F = q.update_cov_with_F;
+    if (m->slab) {
+        SlabFlags* fl = reinterpret_cast<SlabFlags*>(m->xbuf);
+        t.slab_step = &fl->step; t.slab_err = &fl->error;
+        t.base_lo = m->peer_xbuf[0] ? m->slab_x0 - m->slab_slack : -(1 << 30);
+        t.base_hi = m->peer_xbuf[1] ? m->slab_x1 + m->slab_slack : (1 << 30);
+    }
     return t;
 }
 

@@ -128,7 +128,8 @@ def _cuda_solver(fields, idx, capacity):
 
     def put(fid, arr, dtype=torch.float32):
         t = s._t[fid]
-        t.view(capacity, -1)[:n] = torch.as_tensor(np.asarray(arr)[idx].reshape(n, -1), dtype=dtype, device=dev)
+        if n:      # a slab may start empty (particles arrive by migration)
+            t.view(capacity, -1)[:n] = torch.as_tensor(np.asarray(arr)[idx].reshape(n, -1), dtype=dtype, device=dev)
 
     for fid in ("X", "V", "F", "F_TRIAL", "VOL", "DENSITY", "E", "NU"):
         put(fid, fields[fid])
@@ -177,7 +178,7 @@ def test_cuda_slabs_match_single_domain_cuda(world, migrate_every):
     fields = make_scene(N, G, LIM)
     steps = 60
     ranks, finish_setup = _cuda_cluster(fields, world, migrate_every,
-                                        bounds=None if world < 4 else [(0, 5), (5, 9), (9, 13), (13, 16)])
+                                        bounds=None if world != 3 else [(0, 6), (6, 10), (10, 16)])       # unequal slabs too
     whole = _cuda_solver(fields, np.arange(N), N)
     finish_setup(whole)
     whole.p2g2p_n(steps, DT)
