@@ -170,7 +170,9 @@ def run_mpm_slab_block(args, rank, world, dev, pk):
     from pixie_b200.mpm_slab import DistSlabDriver, FusedSlabBackend, SlabRank, balanced_slab_bounds
     from pixie_b200.mpm_solver_warp import MPM_Simulator_WARP
     from pixie_b200.synthetic import synthetic_scene
-    n, G, lim, dt = args.slab_particles, args.slab_grid, 2.0, 1e-4
+    # dt: the scene's stiffest particles (E = 10^6.5, rho = 200) have a wave speed of 126 m/s; with dx = 2/256 the explicit update
+    # needs c dt / dx < 1, i.e. dt < 6e-5 (the 64^3 scene of configs[2] runs at 1e-4 with dx = 2/64)
+    n, G, lim, dt = args.slab_particles, args.slab_grid, 2.0, 2e-5
     slack, migrate_every = 2, 25
     sc = synthetic_scene(n, G, seed=0, materials=(0,))              # identical on every rank (seeded)
     base = (sc["x"][:, 0].astype(np.float32) * np.float32(G / lim) - np.float32(0.5)).astype(np.int32)
@@ -227,6 +229,10 @@ def run_mpm_slab_block(args, rank, world, dev, pk):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    xs = s.mpm_state.particle_x.numpy()[: active()]
+    fin = torch.tensor([float(np.isfinite(xs).all() and xs.min() > 0.3 and xs.max() < 1.7)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(fin, op=dist.ReduceOp.MIN)
     if rank != 0:
         return None
     ms = float(t.item())
@@ -236,7 +242,7 @@ def run_mpm_slab_block(args, rank, world, dev, pk):
     ext = [int(np.floor(sc["x"][:, a].max() * G / lim - 0.5)) + 3 - int(np.floor(sc["x"][:, a].min() * G / lim - 0.5)) + 4 for a in (1, 2)]
     return {"metric": "mpm_particle_steps_per_s", "value": n * sub / (ms * 1e-3), "unit": "particle-steps/s", "us_per_substep": ms / sub * 1e3,
             "scaling": "strong", "substeps": sub, "particles": n, "grid": G, "particles_after": int(cnt.item()),
-            "max_particles_per_rank": int(mx.item()), "slab_bounds": bounds, "slack_planes": slack, "migrate_every": migrate_every,
+            "state_finite_and_in_bounds": bool(fin.item() > 0), "dt": dt, "max_particles_per_rank": int(mx.item()), "slab_bounds": bounds, "slack_planes": slack, "migrate_every": migrate_every,
             "exchange": ("none (undivided scene)" if world == 1 else
                          "device-side: halo kernel reads the neighbour's partial sums over NVLink (cudaIpc-mapped grids, flag handshake); "
                          "migration over NCCL send/recv"),

@@ -224,19 +224,10 @@ int pixie_mpm_select_cylinder(pixie_mpm_t h, const float point[3], const float n
  * arrays stay in the caller's order and are what every other entry point reads): pixie_mpm_sync writes the results back
  * into the bound arrays and must precede any read of them; every other entry point that touches the bound arrays calls it
  * internally. After a sync the caller may modify its arrays: the next step re-reads them. It is a no-op when nothing was
- * stepped since the last sync and on the direct path (slab-decomposed runs, PIXIE_MPM_DIRECT=1), which works in place. */
+ * stepped since the last sync. */
 int pixie_mpm_sync(pixie_mpm_t h, void* stream);
-/* ---- Spatially sharded rollout (BASELINE config 5: one large scene, slab decomposition along x; no reference
- * counterpart — the reference hard-wires "cuda:0", gs_simulation.py:441). One handle per rank holds the particles whose
- * base cell lies in the rank's slab. The caller owns the {mv.xyz, m} grid (float4[n_grid^3], zero-initialised, x slowest
- * so a plane range is one contiguous block), restricts the grid update to its planes, and between _scatter and _finish
- * adds the neighbours' partial sums of the shared planes (NCCL send/recv, pixie_b200/mpm_slab.py). Particles that
- * leave the slab are moved by the caller: the live particles are the prefix [0, n_active) of the bound arrays. */
-int pixie_mpm_bind_grid(pixie_mpm_t h, void* mv4_dev);
-int pixie_mpm_set_slab(pixie_mpm_t h, int x_begin, int x_end);
+/* Live particles = the prefix [0, n_active) of the bound arrays (slab runs migrate particles between ranks). */
 int pixie_mpm_set_active_count(pixie_mpm_t h, int n_active);
-int pixie_mpm_substep_scatter(pixie_mpm_t h, double dt, void* stream);   /* particle BCs + stress + p2g     */
-int pixie_mpm_substep_finish(pixie_mpm_t h, double dt, void* stream);    /* grid update + g2p + clock      */
 /* Borrowed pointers to the grid arrays owned by the handle: grid_m [n^3], grid_v_in / grid_v_out
  * [n^3][3] as left by the last substep (for tests). */
 int pixie_mpm_grid_ptrs(pixie_mpm_t h, float** grid_mv4, float** grid_v_out);

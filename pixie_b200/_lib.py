@@ -91,11 +91,7 @@ _SIGNATURES = {
     "pixie_particle_volume": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p]),
     "pixie_frame_transform": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int,
                                         C.c_void_p, C.c_void_p, C.c_void_p]),
-    "pixie_mpm_bind_grid": (C.c_int, [C.c_void_p, C.c_void_p]),
-    "pixie_mpm_set_slab": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "pixie_mpm_set_active_count": (C.c_int, [C.c_void_p, C.c_int]),
-    "pixie_mpm_substep_scatter": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p]),
-    "pixie_mpm_substep_finish": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p]),
     "pixie_mpm_grid_ptrs": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     "pixie_mpm_launch_count": (C.c_longlong, [C.c_void_p]),
     "pixie_mpm_exchange_buffer": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),

@@ -170,11 +170,7 @@ int pixie_mpm_select_cylinder(pixie_mpm_t h, const float point[3], const float n
     MPM_CALL(pixie::mpm_select_cylinder(h->m, point, normal, hh, radius, mask, (cudaStream_t)s));
 }
 int pixie_mpm_sync(pixie_mpm_t h, void* s) { MPM_CALL(pixie::mpm_sync(h->m, (cudaStream_t)s)); }
-int pixie_mpm_bind_grid(pixie_mpm_t h, void* mv4_dev) { MPM_CALL(pixie::mpm_bind_grid(h->m, mv4_dev)); }
-int pixie_mpm_set_slab(pixie_mpm_t h, int x_begin, int x_end) { MPM_CALL(pixie::mpm_set_slab(h->m, x_begin, x_end)); }
 int pixie_mpm_set_active_count(pixie_mpm_t h, int n_active) { MPM_CALL(pixie::mpm_set_active_count(h->m, n_active)); }
-int pixie_mpm_substep_scatter(pixie_mpm_t h, double dt, void* s) { MPM_CALL(pixie::mpm_substep_scatter(h->m, dt, (cudaStream_t)s)); }
-int pixie_mpm_substep_finish(pixie_mpm_t h, double dt, void* s) { MPM_CALL(pixie::mpm_substep_finish(h->m, dt, (cudaStream_t)s)); }
 int pixie_mpm_grid_ptrs(pixie_mpm_t h, float** mv4, float** v4) { MPM_CALL(pixie::mpm_grid_ptrs(h->m, mv4, v4)); }
 int pixie_mpm_exchange_buffer(pixie_mpm_t h, void** base, size_t* bytes) { MPM_CALL(pixie::mpm_exchange_buffer(h->m, base, bytes)); }
 int pixie_mpm_slab_attach(pixie_mpm_t h, int x0, int x1, int slack, const void* left, const void* right) {

@@ -2,18 +2,15 @@
 // (third_party/PhysGaussian/mpm_solver_warp/mpm_solver_warp.py:514-637) and the Warp kernels it
 // launches (mpm_utils.py:295-588, BC closures mpm_solver_warp.py:785-1179).
 //
-// Two paths:
-//   default ("fused", mpm_fused.cuh): a private cell-sorted SoA copy of the particle state and two launches per
-//     substep (particle kernel: g2p(i) + BCs/stress/p2g(i+1); grid kernel over the particles' node box), replayed from
-//     a CUDA graph of 50 substeps with the simulation clock on the device;
-//   direct (this file; slab-decomposed runs, PIXIE_MPM_DIRECT=1): four launches per substep on the caller's arrays
-//     mpm_stress  : [impulse / Dirichlet particle BCs] -> return mapping + Kirchhoff stress
-//     mpm_scatter : warp-aggregated p2g (one red.global.add.v4.f32 per run and node: grid node = float4 {mv.xyz, m})
-//     mpm_grid    : normalise + gravity + damping + every grid BC (from a device BC table, registration
-//                   order) -> grid_v; clears the {mv, m} node it just consumed (zero_grid fused away)
-//     mpm_g2p     : gather, x/v/C/F_trial update, optional covariance update; thread 0 advances the
-//                   simulation clock and moves the cuboid colliders (the reference's host-side
-//                   `modify`, mpm_solver_warp.py:899-905, and `self.time += dt`, :637)
+// One substep = two launches (mpm_fused.cuh), replayed from CUDA graphs with the simulation clock on the device:
+//   mpm_fused_kernel   : g2p(i) -> particle BCs / return map / stress(i+1) -> warp-aggregated p2g(i+1), on a private
+//                        cell-sorted SoA copy of the particle state (grid node = float4 {mv.xyz, m})
+//   mpm_gridbox_kernel : normalise + gravity + damping + every grid BC (device BC table, registration order) -> grid_v over
+//                        the particles' node box; clears the {mv, m} nodes it consumed (zero_grid fused away); advances the
+//                        clock and the moving cuboids (the reference's host-side `modify`, mpm_solver_warp.py:899-905,
+//                        and `self.time += dt`, :637)
+// Slab-decomposed runs add mpm_halo_kernel between the two (device-side overlap exchange).  This file holds the small setup /
+// export kernels (on the caller's arrays) and the host side.
 #include "mpm.cuh"
 #include "mpm_math.cuh"
 #include "ptx.cuh"
@@ -50,7 +47,6 @@ struct DevState {
     float *x, *v, *F, *F_trial, *C, *stress, *R, *cov, *init_cov;
     float *vol, *mass, *density, *E, *nu, *mu, *lam, *bulk, *yield_stress;
     int *material, *selection;
-    const int* order;   // thread i of p2g handles particle order[i] (cell-sorted, possibly a few substeps stale), or nullptr
     // grid
     float4* grid_mv;    // {momentum.xyz, mass}
     float4* grid_v;     // {velocity.xyz, 0}
@@ -60,12 +56,10 @@ struct DevState {
     int n_bc;
     // scalars
     int n, n_grid;
-    int x_begin, x_end;       // grid planes updated by mpm_grid_kernel
     float dx, inv_dx;
     float gx, gy, gz;
     float rpic_damping, grid_v_damping_scale, alpha, hardening, xi, plastic_viscosity, softening;
     int update_cov_with_F;
-    int scatter_slices;       // 3: one thread per (particle, x-slice of the stencil); 1: one thread per particle
 };
 
 __device__ __forceinline__ M3 load_m3(const float* p, int i) {
@@ -77,352 +71,6 @@ __device__ __forceinline__ M3 load_m3(const float* p, int i) {
 __device__ __forceinline__ void store_m3(float* p, int i, const M3& a) {
 #pragma unroll
     for (int k = 0; k < 9; ++k) p[(size_t)i * 9 + k] = a.m[k];
-}
-
-struct Weights { int bx, by, bz; float fx[3]; float w[3][3]; float dw[3][3]; };   // [axis][node]
-
-__device__ __forceinline__ Weights bspline_t(float inv_dx, float px, float py, float pz) {
-    Weights W;
-    const float g[3] = {px * inv_dx, py * inv_dx, pz * inv_dx};
-    int b[3];
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-        b[a] = (int)(g[a] - 0.5f);                      // wp.int truncates toward zero (mpm_utils.py:344-346)
-        const float fx = g[a] - (float)b[a];
-        W.fx[a] = fx;
-        const float wa = 1.5f - fx, wb = fx - 1.0f, wc = fx - 0.5f;
-        W.w[a][0] = wa * wa * 0.5f;
-        W.w[a][1] = 0.f - wb * wb + 0.75f;
-        W.w[a][2] = wc * wc * 0.5f;
-        W.dw[a][0] = fx - 1.5f;
-        W.dw[a][1] = -2.0f * (fx - 1.0f);
-        W.dw[a][2] = fx - 0.5f;
-    }
-    W.bx = b[0]; W.by = b[1]; W.bz = b[2];
-    return W;
-}
-__device__ __forceinline__ Weights bspline(const DevState& s, float px, float py, float pz) { return bspline_t(s.inv_dx, px, py, pz); }
-
-// ------------------------------------------------------------------------------------------ p2g
-// Substep part 1, one thread per particle: pre-p2g particle operations, return mapping, stress.
-// Writes v (if a BC changed it), F, stress (and yield_stress / mu / lam where a return map updates them).
-// The scatter itself is mpm_scatter_kernel: at 1e5 particles a single kernel that does both is one long dependent
-// instruction stream on ~20 warps per SM (r01 ncu: 4600 instructions per thread, issue slots 36 % used).
-__global__ void __launch_bounds__(128)
-mpm_stress_kernel(const DevState s, const float dt) {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= s.n) return;
-    const bool live = true;
-    const float time = (float)(*s.time);
-    float vx = s.v[3 * p], vy = s.v[3 * p + 1], vz = s.v[3 * p + 2];
-    const float px = s.x[3 * p], py = s.x[3 * p + 1], pz = s.x[3 * p + 2];
-    const float mass = s.mass[p];
-
-    // ---- pre-p2g particle operations: all impulses first, then all velocity modifiers
-    //      (mpm_solver_warp.py:528-547)
-    bool v_dirty = false;
-    for (int k = 0; k < s.n_bc; ++k) {
-        const DevBC& bc = s.bcs[k];
-        if (bc.kind != PIXIE_BC_IMPULSE) continue;
-        if (time >= bc.start_time && time < bc.end_time && bc.mask[p] == 1) {
-            vx = vx + (bc.velocity[0] / mass) * dt;      // apply_force :1015-1027 (force stored in velocity[])
-            vy = vy + (bc.velocity[1] / mass) * dt;
-            vz = vz + (bc.velocity[2] / mass) * dt;
-            v_dirty = true;
-        }
-    }
-    for (int k = 0; k < s.n_bc; ++k) {
-        const DevBC& bc = s.bcs[k];
-        if (bc.kind == PIXIE_BC_VELOCITY_TRANSLATION) {
-            if (time >= bc.start_time && time < bc.end_time && bc.mask[p] == 1) {
-                vx = bc.velocity[0]; vy = bc.velocity[1]; vz = bc.velocity[2];
-                v_dirty = true;
-            }
-        } else if (bc.kind == PIXIE_BC_VELOCITY_ROTATION) {
-            if (time >= bc.start_time && time < bc.end_time && bc.mask[p] == 1) {
-                // modify_particle_v_before_p2g :1137-1179
-                const float ox = px - bc.point[0], oy = py - bc.point[1], oz = pz - bc.point[2];
-                const float on = ox * bc.normal[0] + oy * bc.normal[1] + oz * bc.normal[2];
-                const float hx = ox - on * bc.normal[0], hy = oy - on * bc.normal[1], hz = oz - on * bc.normal[2];
-                const float hd = sqrtf(hx * hx + hy * hy + hz * hz);
-                const float cosine = (ox * bc.h1[0] + oy * bc.h1[1] + oz * bc.h1[2]) / hd;
-                float theta = acosf(cosine);
-                if (!(ox * bc.h2[0] + oy * bc.h2[1] + oz * bc.h2[2] > 0.f)) theta = -theta;
-                const float a1 = -hd * sinf(theta) * bc.rotation_scale;
-                const float a2 = hd * cosf(theta) * bc.rotation_scale;
-                const float av = bc.translation_scale;
-                vx = a1 * bc.h1[0] + a2 * bc.h2[0] + av * bc.normal[0];
-                vy = a1 * bc.h1[1] + a2 * bc.h2[1] + av * bc.normal[1];
-                vz = a1 * bc.h1[2] + a2 * bc.h2[2] + av * bc.normal[2];
-                v_dirty = true;
-            }
-        }
-    }
-    if (v_dirty && live) { s.v[3 * p] = vx; s.v[3 * p + 1] = vy; s.v[3 * p + 2] = vz; }
-
-    if (s.selection[p] != 0) return;
-    const bool contrib = true;
-
-    // ---- compute_stress_from_F_trial (mpm_utils.py:467-526)
-    const int material = s.material[p];
-    float mu = s.mu[p], lam = s.lam[p];
-    const M3 Ft = load_m3(s.F_trial, p);
-    M3 F = Ft;
-    if (material == 1) {
-        float ys = s.yield_stress[p];
-        const float ys0 = ys;
-        F = return_von_mises(Ft, mu, lam, ys, s.hardening, s.xi, false, 0.f, mu, lam);
-        if (ys != ys0 && contrib) s.yield_stress[p] = ys;
-    } else if (material == 2) {
-        F = return_sand(Ft, mu, lam, s.alpha);
-    } else if (material == 3) {
-        F = return_viscoplastic(Ft, mu, s.yield_stress[p], s.plastic_viscosity, dt);
-    } else if (material == 5) {
-        float ys = s.yield_stress[p];
-        const float ys0 = ys, mu0 = mu;
-        F = return_von_mises(Ft, mu, lam, ys, s.hardening, s.xi, true, s.softening, mu, lam);
-        if (ys != ys0 && contrib) s.yield_stress[p] = ys;
-        if (mu != mu0 && contrib) { s.mu[p] = mu; s.lam[p] = lam; }
-    }
-    if (contrib) store_m3(s.F, p, F);
-    const float J = m3_det(F);
-    M3 tau = m3_zero();
-    if (material == 6) {
-        tau = stress_water(J, s.bulk[p]);
-    } else if (material == 0 || material == 5) {
-        // fixed-corotated stress needs only R = U V^T: Newton polar iteration, SVD only if it does not converge
-        M3 R;
-        if (polar_rotation(F, R)) tau = stress_fcr_R(F, R, J, mu, lam);
-        else { M3 U, V; V3 sig; svd3(F, U, sig, V); tau = stress_fcr(F, U, V, J, mu, lam); }
-    } else if (material >= 1 && material <= 3) {
-        M3 U, V; V3 sig;
-        svd3(F, U, sig, V);
-        if (material == 1 || material == 3) tau = stress_stvk(F, U, V, sig, mu, lam);
-        else tau = stress_drucker_prager(F, U, V, sig, mu, lam);
-    }
-    {   // enforce symmetry
-        const M3 tt = m3_t(tau);
-#pragma unroll
-        for (int i = 0; i < 9; ++i) tau.m[i] = (tau.m[i] + tt.m[i]) / 2.0f;
-    }
-    if (contrib) store_m3(s.stress, p, tau);
-}
-
-// Substep part 2: scatter of slice i = blockIdx.y of the 3x3x3 stencil (9 nodes) with warp-aggregated atomics.
-// Threads walk the particles in cell order (`s.order`), so the lanes of a warp hold runs of particles with the SAME base
-// cell = the same target nodes; each run (chopped at 8 lanes) is summed with 3 segmented shuffle steps per value and only
-// the run's first lane issues the red.global.add.v4. Runs are found from the keys the lanes compute THIS substep, so a
-// stale order costs efficiency, never correctness. (mpm_utils.py:338-394)
-template <int kSlices>
-__global__ void __launch_bounds__(128)
-mpm_scatter_kernel(const DevState s, const float dt) {
-    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = tid < s.n;
-    const int p = live ? (s.order ? s.order[tid] : tid) : 0;
-    const bool contrib = live && s.selection[p] == 0;
-    const float vx = s.v[3 * p], vy = s.v[3 * p + 1], vz = s.v[3 * p + 2];
-    const float px = s.x[3 * p], py = s.x[3 * p + 1], pz = s.x[3 * p + 2];
-    const float mass = s.mass[p];
-    const M3 tau = load_m3(s.stress, p);
-    const Weights W = bspline(s, px, py, pz);
-    M3 C = load_m3(s.C, p);
-    {
-        const float r = s.rpic_damping;
-        const M3 Ct = m3_t(C);
-        M3 Cn;
-#pragma unroll
-        for (int i = 0; i < 9; ++i) Cn.m[i] = (1.0f - r) * C.m[i] + r / 2.0f * (C.m[i] - Ct.m[i]);
-        C = (r < -0.001f) ? m3_zero() : Cn;
-    }
-    const float vol = s.vol[p];
-    const int n = s.n_grid;
-
-    // runs of equal base cell among consecutive lanes, chopped at 8
-    const unsigned full = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    const int key = contrib ? (W.bx * n + W.by) * n + W.bz : -1 - lane;
-    const int kprev = __shfl_up_sync(full, key, 1);
-    bool head = (lane == 0) || (key != kprev);
-    unsigned H = __ballot_sync(full, head);
-    const int hl = 31 - __clz(H & (0xffffffffu >> (31 - lane)));     // head lane of my run
-    head = head || (((lane - hl) & 7) == 0);
-    H = __ballot_sync(full, head);
-    const unsigned above = H & ~((2u << lane) - 1u);                  // heads strictly above this lane
-    const int seg_end = above ? (__ffs(above) - 2) : 31;              // last lane of my segment
-    const bool c1 = lane + 1 <= seg_end, c2 = lane + 2 <= seg_end, c4 = lane + 4 <= seg_end;
-    auto segsum = [&](float v) {
-        float t = __shfl_down_sync(full, v, 1); if (c1) v += t;
-        t = __shfl_down_sync(full, v, 2); if (c2) v += t;
-        t = __shfl_down_sync(full, v, 4); if (c4) v += t;
-        return v;
-    };
-#pragma unroll
-    for (int ii = 0; ii < (kSlices == 1 ? 3 : 1); ++ii) {
-        const int i = kSlices == 1 ? ii : (int)blockIdx.y;
-        // slice weights selected without dynamic indexing (keeps W in registers)
-        const float w0i = i == 0 ? W.w[0][0] : (i == 1 ? W.w[0][1] : W.w[0][2]);
-        const float dw0i = i == 0 ? W.dw[0][0] : (i == 1 ? W.dw[0][1] : W.dw[0][2]);
-#pragma unroll
-        for (int j = 0; j < 3; ++j)
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                const int ix = W.bx + i, iy = W.by + j, iz = W.bz + k;
-                // the reference indexes out of bounds here (no checks); we drop the node. Same verdict for a whole run.
-                const bool inb = contrib && (unsigned)ix < (unsigned)n && (unsigned)iy < (unsigned)n && (unsigned)iz < (unsigned)n;
-                const V3 dpos = {((float)i - W.fx[0]) * s.dx, ((float)j - W.fx[1]) * s.dx, ((float)k - W.fx[2]) * s.dx};
-                const float weight = w0i * W.w[1][j] * W.w[2][k];
-                const V3 dweight = {dw0i * W.w[1][j] * W.w[2][k] * s.inv_dx,
-                                    w0i * W.dw[1][j] * W.w[2][k] * s.inv_dx,
-                                    w0i * W.w[1][j] * W.dw[2][k] * s.inv_dx};
-                const V3 sd = m3_mulv(tau, dweight);
-                const V3 cd = m3_mulv(C, dpos);
-                const float wm = inb ? weight * mass : 0.f;
-                float ax = inb ? wm * (vx + cd.x) + dt * (-vol * sd.x) : 0.f;
-                float ay = inb ? wm * (vy + cd.y) + dt * (-vol * sd.y) : 0.f;
-                float az = inb ? wm * (vz + cd.z) + dt * (-vol * sd.z) : 0.f;
-                float aw = wm;
-                ax = segsum(ax); ay = segsum(ay); az = segsum(az); aw = segsum(aw);
-                if (head && inb) {
-                    float* node = reinterpret_cast<float*>(s.grid_mv + ((size_t)ix * n + iy) * n + iz);
-                    ptx::red_add_v4(node, ax, ay, az, aw);
-                }
-            }
-    }
-}
-
-// ------------------------------------------------------------------------------------------ grid
-__global__ void __launch_bounds__(256)
-mpm_grid_kernel(const DevState s, const float dt) {
-    const int n = s.n_grid;
-    const size_t first = (size_t)s.x_begin * n * n, total = (size_t)s.x_end * n * n;
-    const size_t idx = first + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= total) return;
-    const int gz = (int)(idx % n), gy = (int)((idx / n) % n), gx = (int)(idx / ((size_t)n * n));
-    const float time = (float)(*s.time);
-    const float4 mv = s.grid_mv[idx];
-    float vx = 0.f, vy = 0.f, vz = 0.f;
-    if (mv.w > 1e-15f) {                                   // grid_normalization_and_gravity :398-409
-        const float inv = 1.0f / mv.w;
-        vx = mv.x * inv + dt * s.gx;
-        vy = mv.y * inv + dt * s.gy;
-        vz = mv.z * inv + dt * s.gz;
-    }
-    if (s.grid_v_damping_scale < 1.0f) {                   // add_damping_via_grid :583-588 (only if < 1)
-        vx *= s.grid_v_damping_scale; vy *= s.grid_v_damping_scale; vz *= s.grid_v_damping_scale;
-    }
-    for (int k = 0; k < s.n_bc; ++k) {
-        const DevBC& bc = s.bcs[k];
-        const bool active = time >= bc.start_time && time < bc.end_time;
-        if (bc.kind == PIXIE_BC_SURFACE_COLLIDER) {        // :785-840
-            if (active) {
-                const float ox = (float)gx * s.dx - bc.point[0], oy = (float)gy * s.dx - bc.point[1], oz = (float)gz * s.dx - bc.point[2];
-                const float dotp = ox * bc.normal[0] + oy * bc.normal[1] + oz * bc.normal[2];
-                if (dotp < 0.0f) {
-                    if (bc.surface_type == 11) {
-                        const float zz = (float)gz * s.dx;
-                        if (zz < 0.4f || zz > 0.53f) { vx = 0.f; vy = 0.f; vz = 0.f; }
-                        else { vx = vx * 0.3f; vy = 0.0f * 0.3f; vz = vz * 0.3f; }
-                    } else {
-                        // sticky -> 0; slip / separate: the reference computes the projected velocity and
-                        // then overwrites the node with zero (:838-840)
-                        vx = 0.f; vy = 0.f; vz = 0.f;
-                    }
-                }
-            }
-        } else if (bc.kind == PIXIE_BC_CUBOID) {           // :874-897
-            if (active) {
-                const float ox = (float)gx * s.dx - bc.point[0], oy = (float)gy * s.dx - bc.point[1], oz = (float)gz * s.dx - bc.point[2];
-                if (fabsf(ox) < bc.size[0] && fabsf(oy) < bc.size[1] && fabsf(oz) < bc.size[2]) {
-                    vx = bc.velocity[0]; vy = bc.velocity[1]; vz = bc.velocity[2];
-                }
-            } else if (bc.reset == 1) {
-                if (time < bc.end_time + 15.0f * dt) { vx = 0.f; vy = 0.f; vz = 0.f; }
-            }
-        } else if (bc.kind == PIXIE_BC_BOUNDING_BOX) {     // :917-974
-            if (active) {
-                const int padding = 3;
-                if (gx < padding && vx < 0.f) vx = 0.f;
-                if (gx >= n - padding && vx > 0.f) vx = 0.f;
-                if (gy < padding && vy < 0.f) vy = 0.f;
-                if (gy >= n - padding && vy > 0.f) vy = 0.f;
-                if (gz < padding && vz < 0.f) vz = 0.f;
-                if (gz >= n - padding && vz > 0.f) vz = 0.f;
-            }
-        }
-    }
-    s.grid_v[idx] = make_float4(vx, vy, vz, 0.f);
-    if (mv.x != 0.f || mv.y != 0.f || mv.z != 0.f || mv.w != 0.f) s.grid_mv[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
-}
-
-// ------------------------------------------------------------------------------------------ g2p
-__global__ void __launch_bounds__(128)
-mpm_g2p_kernel(const DevState s, const float dt, const double dt_d) {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p < s.n && s.selection[p] == 0) {
-        const float px = s.x[3 * p], py = s.x[3 * p + 1], pz = s.x[3 * p + 2];
-        const Weights W = bspline(s, px, py, pz);
-        const int n = s.n_grid;
-        float nvx = 0.f, nvy = 0.f, nvz = 0.f;
-        M3 nC = m3_zero(), nF = m3_zero();
-#pragma unroll
-        for (int i = 0; i < 3; ++i)
-#pragma unroll
-            for (int j = 0; j < 3; ++j)
-#pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    const int ix = W.bx + i, iy = W.by + j, iz = W.bz + k;
-                    float4 gv = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if ((unsigned)ix < (unsigned)n && (unsigned)iy < (unsigned)n && (unsigned)iz < (unsigned)n)
-                        gv = s.grid_v[((size_t)ix * n + iy) * n + iz];
-                    const float dp[3] = {(float)i - W.fx[0], (float)j - W.fx[1], (float)k - W.fx[2]};
-                    const float weight = W.w[0][i] * W.w[1][j] * W.w[2][k];
-                    const float dwv[3] = {W.dw[0][i] * W.w[1][j] * W.w[2][k] * s.inv_dx,
-                                          W.w[0][i] * W.dw[1][j] * W.w[2][k] * s.inv_dx,
-                                          W.w[0][i] * W.w[1][j] * W.dw[2][k] * s.inv_dx};
-                    nvx = nvx + gv.x * weight; nvy = nvy + gv.y * weight; nvz = nvz + gv.z * weight;
-                    const float cw = weight * s.inv_dx * 4.0f;
-                    const float g3[3] = {gv.x, gv.y, gv.z};
-#pragma unroll
-                    for (int r = 0; r < 3; ++r)
-#pragma unroll
-                        for (int c = 0; c < 3; ++c) {
-                            nC.m[3 * r + c] = nC.m[3 * r + c] + (g3[r] * dp[c]) * cw;
-                            nF.m[3 * r + c] = nF.m[3 * r + c] + g3[r] * dwv[c];
-                        }
-                }
-        s.v[3 * p] = nvx; s.v[3 * p + 1] = nvy; s.v[3 * p + 2] = nvz;
-        s.x[3 * p] = px + dt * nvx; s.x[3 * p + 1] = py + dt * nvy; s.x[3 * p + 2] = pz + dt * nvz;
-        store_m3(s.C, p, nC);
-        M3 A = m3_ident();
-#pragma unroll
-        for (int i = 0; i < 9; ++i) A.m[i] += nF.m[i] * dt;
-        store_m3(s.F_trial, p, m3_mul(A, load_m3(s.F, p)));
-        if (s.update_cov_with_F) {                          // update_cov :315-335
-            float* cv = s.cov + (size_t)p * 6;
-            M3 cn;
-            cn.m[0] = cv[0]; cn.m[1] = cv[1]; cn.m[2] = cv[2]; cn.m[3] = cv[1]; cn.m[4] = cv[3]; cn.m[5] = cv[4];
-            cn.m[6] = cv[2]; cn.m[7] = cv[4]; cn.m[8] = cv[5];
-            const M3 a = m3_mul(nF, cn), b = m3_mul_t(cn, nF);
-            M3 c1;
-#pragma unroll
-            for (int i = 0; i < 9; ++i) c1.m[i] = cn.m[i] + dt * (a.m[i] + b.m[i]);
-            cv[0] = c1.m[0]; cv[1] = c1.m[1]; cv[2] = c1.m[2]; cv[3] = c1.m[4]; cv[4] = c1.m[5]; cv[5] = c1.m[8];
-        }
-    }
-    // ---- substep epilogue: nothing in this kernel reads the clock or the BC table
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        const double t = *s.time;
-        for (int k = 0; k < s.n_bc; ++k) {
-            DevBC& bc = s.bcs[k];
-            if (bc.kind == PIXIE_BC_CUBOID && t >= (double)bc.start_time && t < (double)bc.end_time) {
-                // modify(): Python-float arithmetic, stored back as fp32 (mpm_solver_warp.py:899-905)
-                bc.point[0] = (float)((double)bc.point[0] + dt_d * (double)bc.velocity[0]);
-                bc.point[1] = (float)((double)bc.point[1] + dt_d * (double)bc.velocity[1]);
-                bc.point[2] = (float)((double)bc.point[2] + dt_d * (double)bc.velocity[2]);
-            }
-        }
-        *s.time = t + dt_d;
-    }
 }
 
 // ------------------------------------------------------------------------------------------ setup kernels
@@ -508,16 +156,6 @@ __global__ void mpm_select_cyl_kernel(const DevState s, float3 point, float3 nor
 
 #include "mpm_fused.cuh"
 
-// base-cell key of every live particle (+ identity index), input of the radix sort that produces DevState::order
-__global__ void mpm_cell_key_kernel(const float* __restrict__ x, int n, float inv_dx, int n_grid, int* __restrict__ keys, int* __restrict__ idx) {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n) return;
-    const Weights W = bspline_t(inv_dx, x[3 * p], x[3 * p + 1], x[3 * p + 2]);
-    const int bx = min(max(W.bx, 0), n_grid - 1), by = min(max(W.by, 0), n_grid - 1), bz = min(max(W.bz, 0), n_grid - 1);
-    keys[p] = (bx * n_grid + by) * n_grid + bz;
-    idx[p] = p;
-}
-
 }  // namespace
 
 // ============================================================================================ host
@@ -525,34 +163,26 @@ struct Mpm {
     int n = 0, n_grid = 0;
     int n_active = 0;                  // particles [0, n_active) are live (slab mode migrates particles between ranks)
     int x_begin = 0, x_end = 0;        // grid planes this instance updates ([0, n_grid) unless slab-decomposed)
-    bool grid_borrowed = false;        // grid_mv belongs to the caller (pixie_mpm_bind_grid)
     float grid_lim = 1.f;
     void* fields[PIXIE_MPM_FIELD_COUNT] = {nullptr};
     pixie_mpm_params params{};
     std::vector<DevBC> bcs;
     float4* grid_mv = nullptr;
     float4* grid_v = nullptr;
-    double* d_time = nullptr;          // direct path clock
     DevBC* d_bcs = nullptr;
-    // direct path: CUDA graph of a batch of substeps, keyed by dt and the state snapshot it was captured with
-    cudaGraphExec_t graph = nullptr;
-    double graph_dt = 0;
-    bool graph_valid = false;
-    // fused path: a few cached graphs keyed by (substep count, clock parity, dt)
+    bool graph_valid = false;          // false: parameters / BCs changed, captured launches are stale
+    // a few cached CUDA graphs keyed by (substep count, clock parity, dt)
     static constexpr int kGraphSlots = 4;
     struct GraphSlot { cudaGraphExec_t exec = nullptr; int count = 0, parity = 0, launches = 0; double dt = 0; } graphs[kGraphSlots];
     int graph_next = 0;
     std::string error;
 
-    // ---- cell order (radix sort of base-cell keys): indirection of the direct path, physical order of the fused path
+    // ---- cell order (radix sort of base-cell keys) = physical order of the private particle copy
     int *cell_order = nullptr, *cell_keys = nullptr, *cell_keys_sorted = nullptr, *cell_idx = nullptr;
     void* cub_tmp = nullptr;
     size_t cub_bytes = 0;
-    bool order_valid = false;
-    int steps_since_order = 0;
 
     // ---- fused path (mpm_fused.cuh): private cell-sorted SoA copy of the particle state
-    bool fused = true;                 // false: four-kernel path on the caller's arrays (slab-decomposed runs, PIXIE_MPM_DIRECT=1)
     struct FsBuf { float* f = nullptr; int *material = nullptr, *selection = nullptr, *perm = nullptr; } fs[2];
     int cap = 0;
     int* d_box = nullptr;              // [6] node box swept by the grid kernel
@@ -575,8 +205,7 @@ struct Mpm {
     long long launches = 0;            // kernels of this library launched for this handle (bench.py's gpu_launches)
 };
 
-static constexpr int kGraphSteps = 25;         // direct path
-static constexpr int kFusedGraphSteps = 50;    // fused path: substeps per graph replay
+static constexpr int kFusedGraphSteps = 50;    // substeps per graph replay
 static constexpr int kMinGraphSteps = 4;       // shorter batches are launched directly
 static constexpr int kResortEvery = 100;       // substeps between re-sorts; CFL keeps a particle within ~a cell of its slot far longer
 static constexpr int kBoxMargin = 2;           // nodes added around the particles' node box at every sort
@@ -591,10 +220,8 @@ static DevState make_state(Mpm* m) {
     s.lam = f(PIXIE_MPM_LAM); s.bulk = f(PIXIE_MPM_BULK); s.yield_stress = f(PIXIE_MPM_YIELD);
     s.material = reinterpret_cast<int*>(m->fields[PIXIE_MPM_MATERIAL]);
     s.selection = reinterpret_cast<int*>(m->fields[PIXIE_MPM_SELECTION]);
-    s.order = m->order_valid ? m->cell_order : nullptr;
-    s.grid_mv = m->grid_mv; s.grid_v = m->grid_v; s.time = m->d_time; s.bcs = m->d_bcs; s.n_bc = (int)m->bcs.size();
+    s.grid_mv = m->grid_mv; s.grid_v = m->grid_v; s.time = m->tslots; s.bcs = m->d_bcs; s.n_bc = (int)m->bcs.size();
     s.n = m->n_active; s.n_grid = m->n_grid;
-    s.x_begin = m->x_begin; s.x_end = m->x_end;
     // dx, inv_dx exactly as mpm_solver_warp.py:61-66 (Python doubles rounded to fp32 members)
     s.dx = (float)((double)m->grid_lim / (double)m->n_grid);
     s.inv_dx = (float)((double)m->n_grid / (double)m->grid_lim);
@@ -603,7 +230,6 @@ static DevState make_state(Mpm* m) {
     s.rpic_damping = q.rpic_damping; s.grid_v_damping_scale = q.grid_v_damping_scale; s.alpha = q.alpha;
     s.hardening = q.hardening; s.xi = q.xi; s.plastic_viscosity = q.plastic_viscosity; s.softening = q.softening;
     s.update_cov_with_F = q.update_cov_with_F;
-    s.scatter_slices = 1;
     return s;
 }
 
@@ -720,7 +346,6 @@ static int fused_resort(Mpm* m, cudaStream_t st) {
 // sorted state -> caller's arrays (if it is ahead); afterwards the caller may mutate its arrays, so the sorted copy is
 // considered out of date.
 int mpm_sync(Mpm* m, cudaStream_t st) {
-    if (!m->fused) return 0;
     if (m->g2p_pending && m->internal_valid) {        // slab phases: finish the last substep (gather) before anything is read
         fused_launch(m, true, false, true, m->slab_dt, st);
         m->g2p_pending = false;
@@ -833,6 +458,11 @@ static void halo_launch(Mpm* m, cudaStream_t st) {
         a.total[sd] = m->ov_total[sd]; a.ov_lo[sd] = m->ov_lo[sd]; a.ov_hi[sd] = m->ov_hi[sd];
     }
     pdl_launch(mpm_halo_kernel, dim3(148), dim3(256), st, a);
+    pdl_launch(mpm_publish_kernel, dim3(1), dim3(32), st, a.mine, 1);          // halo_done: the neighbours may clear what this rank read
+    m->launches += 2;
+}
+static void publish_scatter(Mpm* m, cudaStream_t st) {
+    pdl_launch(mpm_publish_kernel, dim3(1), dim3(32), st, reinterpret_cast<SlabFlags*>(m->xbuf), 0);
     m->launches += 1;
 }
 
@@ -840,7 +470,7 @@ static void halo_launch(Mpm* m, cudaStream_t st) {
 static void fused_batch(Mpm* m, int count, float dt, double dt_d, cudaStream_t st) {
     fused_launch(m, false, true, count == 1 || m->slab, dt, st);
     for (int i = 0; i < count; ++i) {
-        if (m->slab) halo_launch(m, st);
+        if (m->slab) { publish_scatter(m, st); halo_launch(m, st); }
         gridbox_launch(m, dt, dt_d, st);
         if (i + 1 < count) fused_launch(m, true, true, i + 2 == count || m->slab, dt, st);
         else fused_launch(m, true, false, true, dt, st);
@@ -905,26 +535,6 @@ static int mpm_step_fused(Mpm* m, int n_substeps, double dt_d, cudaStream_t st) 
     return 0;
 }
 
-// leave the fused path for good (slab-decomposed runs drive the four-kernel path on the caller's arrays)
-static int switch_to_direct(Mpm* m) {
-    if (!m->fused) return 0;
-    if (mpm_sync(m, 0)) return 1;
-    cudaDeviceSynchronize();
-    double t = 0;
-    cudaMemcpy(&t, m->tslots + m->tpar, sizeof(double), cudaMemcpyDeviceToHost);
-    cudaMemcpy(m->d_time, &t, sizeof(double), cudaMemcpyHostToDevice);
-    // moved collider points back into the BC table the direct kernels read
-    std::vector<float> pts((size_t)kMaxBC * 3);
-    cudaMemcpy(pts.data(), m->pts + (size_t)m->tpar * kMaxBC * 3, pts.size() * sizeof(float), cudaMemcpyDeviceToHost);
-    for (size_t k = 0; k < m->bcs.size(); ++k) {
-        for (int a = 0; a < 3; ++a) m->bcs[k].point[a] = pts[3 * k + a];
-        cudaMemcpy(m->d_bcs + k, &m->bcs[k], sizeof(DevBC), cudaMemcpyHostToDevice);
-    }
-    m->fused = false;
-    m->graph_valid = false;
-    return 0;
-}
-
 Mpm* mpm_create(int n_particles, int n_grid, float grid_lim, std::string& err) {
     if (n_particles <= 0 || n_grid <= 0) { err = "n_particles and n_grid must be positive"; return nullptr; }
     auto* m = new Mpm();
@@ -941,7 +551,6 @@ Mpm* mpm_create(int n_particles, int n_grid, float grid_lim, std::string& err) {
     const size_t nodes = (size_t)n_grid * n_grid * n_grid;
     if (cudaMalloc(&m->xbuf, sizeof(SlabFlags) + nodes * sizeof(float4)) != cudaSuccess ||
         cudaMalloc(&m->grid_v, nodes * sizeof(float4)) != cudaSuccess ||
-        cudaMalloc(&m->d_time, sizeof(double)) != cudaSuccess ||
         cudaMalloc(&m->d_bcs, kMaxBC * sizeof(DevBC)) != cudaSuccess ||
         cudaMalloc(&m->d_box, 6 * sizeof(int)) != cudaSuccess ||
         cudaMalloc(&m->tslots, 2 * sizeof(double)) != cudaSuccess ||
@@ -953,10 +562,8 @@ Mpm* mpm_create(int n_particles, int n_grid, float grid_lim, std::string& err) {
     m->grid_mv = reinterpret_cast<float4*>(m->xbuf + sizeof(SlabFlags));
     cudaMemset(m->xbuf, 0, sizeof(SlabFlags) + nodes * sizeof(float4));
     cudaMemset(m->grid_v, 0, nodes * sizeof(float4));
-    cudaMemset(m->d_time, 0, sizeof(double));
     cudaMemset(m->tslots, 0, 2 * sizeof(double));
     cudaMemset(m->pts, 0, (size_t)2 * kMaxBC * 3 * sizeof(float));
-    m->fused = getenv("PIXIE_MPM_DIRECT") == nullptr;
     if (const char* a = getenv("PIXIE_MPM_AGG")) m->agg = std::min(3, std::max(0, atoi(a)));
     return m;
 }
@@ -966,11 +573,10 @@ void mpm_destroy(Mpm* m) {
     cudaFree(m->cell_order); cudaFree(m->cell_keys); cudaFree(m->cell_keys_sorted); cudaFree(m->cell_idx); cudaFree(m->cub_tmp);
     for (int b = 0; b < 2; ++b) { cudaFree(m->fs[b].f); cudaFree(m->fs[b].material); cudaFree(m->fs[b].selection); cudaFree(m->fs[b].perm); }
     cudaFree(m->d_box); cudaFree(m->tslots); cudaFree(m->pts);
-    if (m->graph) cudaGraphExecDestroy(m->graph);
     for (auto& g : m->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
     cudaFree(m->xbuf);
     cudaFree(m->ov_total[0]); cudaFree(m->ov_total[1]);
-    cudaFree(m->grid_v); cudaFree(m->d_time); cudaFree(m->d_bcs);
+    cudaFree(m->grid_v); cudaFree(m->d_bcs);
     delete m;
 }
 
@@ -978,7 +584,6 @@ int mpm_bind(Mpm* m, int field, void* ptr) {
     if (field < 0 || field >= PIXIE_MPM_FIELD_COUNT) { m->error = "bad field id"; return 1; }
     if (mpm_sync(m, 0)) return 1;          // flush results into the arrays bound so far before one of them changes
     m->fields[field] = ptr;
-    m->graph_valid = m->fused ? m->graph_valid : false;   // the fused graph only references the private copy
     return 0;
 }
 int mpm_set_params(Mpm* m, const pixie_mpm_params& p) {
@@ -987,9 +592,9 @@ int mpm_set_params(Mpm* m, const pixie_mpm_params& p) {
         // set_parameters_dict re-allocates the grids when n_grid changes (mpm_solver_warp.py:318-343)
         if (m->slab) { m->error = "n_grid cannot change in slab mode"; return 1; }
         cudaDeviceSynchronize();
-        if (!m->grid_borrowed) cudaFree(m->xbuf);
+        cudaFree(m->xbuf);
         cudaFree(m->grid_v);
-        m->xbuf = nullptr; m->grid_borrowed = false;
+        m->xbuf = nullptr;
         const size_t nodes = (size_t)p.n_grid * p.n_grid * p.n_grid;
         if (cudaMalloc(&m->xbuf, sizeof(SlabFlags) + nodes * sizeof(float4)) != cudaSuccess ||
             cudaMalloc(&m->grid_v, nodes * sizeof(float4)) != cudaSuccess) { m->error = "cudaMalloc failed"; return 1; }
@@ -1031,11 +636,10 @@ int mpm_add_bc(Mpm* m, const pixie_mpm_bc& b) {
 int mpm_clear_bcs(Mpm* m) { m->bcs.clear(); m->graph_valid = false; return 0; }
 int mpm_set_time(Mpm* m, double t) {
     const double both[2] = {t, t};
-    if (cudaMemcpy(m->tslots, both, sizeof(both), cudaMemcpyHostToDevice) != cudaSuccess) return 1;
-    return cudaMemcpy(m->d_time, &t, sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess;
+    return cudaMemcpy(m->tslots, both, sizeof(both), cudaMemcpyHostToDevice) != cudaSuccess;
 }
 int mpm_get_time(Mpm* m, double* t) {
-    const double* src = m->fused ? m->tslots + m->tpar : m->d_time;
+    const double* src = m->tslots + m->tpar;
     return cudaMemcpy(t, src, sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess;
 }
 
@@ -1049,82 +653,10 @@ static int check_bound(Mpm* m) {
     return 0;
 }
 
-static constexpr int kReorderEvery = 100;   // direct path: substeps between re-sorts of the order indirection
-
-// (Re)builds Mpm::cell_order from the current positions. Stream-ordered, no host sync: the graph reads the same buffer.
-static int mpm_build_cell_order(Mpm* m, cudaStream_t st) {
-    const int n = m->n_active;
-    if (n <= 0) { m->order_valid = false; return 0; }
-    if (sort_alloc(m)) return 1;
-    const float inv_dx = (float)((double)m->n_grid / (double)m->grid_lim);
-    mpm_cell_key_kernel<<<(n + 255) / 256, 256, 0, st>>>(reinterpret_cast<const float*>(m->fields[PIXIE_MPM_X]), n, inv_dx, m->n_grid, m->cell_keys, m->cell_idx);
-    size_t bytes = m->cub_bytes;
-    if (cub::DeviceRadixSort::SortPairs(m->cub_tmp, bytes, m->cell_keys, m->cell_keys_sorted, m->cell_idx, m->cell_order, n, 0, key_bits(m), st) != cudaSuccess) {
-        m->error = "radix sort failed"; return 1;
-    }
-    m->steps_since_order = 0;
-    if (!m->order_valid) { m->order_valid = true; m->graph_valid = false; }   // DevState::order changes from null to the buffer
-    return 0;
-}
-
-// Threads per block of the per-particle kernels of the direct path
-static int particle_block() {
-    static const int b = getenv("PIXIE_MPM_BLOCK") ? atoi(getenv("PIXIE_MPM_BLOCK")) : 64;
-    return (b == 32 || b == 64 || b == 128) ? b : 64;
-}
-
-static void launch_substep(const DevState& s, float dt, double dt_d, cudaStream_t st) {
-    const int n = s.n;
-    const size_t nodes = (size_t)(s.x_end - s.x_begin) * s.n_grid * s.n_grid;
-    if (n > 0) {
-        const int B = particle_block();
-        mpm_stress_kernel<<<(n + B - 1) / B, B, 0, st>>>(s, dt);
-        mpm_scatter_kernel<1><<<(n + B - 1) / B, B, 0, st>>>(s, dt);
-    }
-    mpm_grid_kernel<<<(unsigned)((nodes + 255) / 256), 256, 0, st>>>(s, dt);
-    mpm_g2p_kernel<<<(std::max(n, 1) + particle_block() - 1) / particle_block(), particle_block(), 0, st>>>(s, dt, dt_d);
-}
-
 int mpm_step(Mpm* m, int n_substeps, double dt_d, cudaStream_t st) {
     if (check_bound(m)) return 1;
     if (n_substeps <= 0) return 0;
-    if (m->fused) return mpm_step_fused(m, n_substeps, dt_d, st);
-    const float dt = (float)dt_d;
-    if ((!m->order_valid || m->steps_since_order >= kReorderEvery) && mpm_build_cell_order(m, st)) return 1;
-    const DevState s = make_state(m);
-    int done = 0;
-    if (n_substeps >= kGraphSteps) {
-        if (!m->graph_valid || m->graph_dt != dt_d) {
-            if (m->graph) { cudaGraphExecDestroy(m->graph); m->graph = nullptr; }
-            cudaStream_t cs;
-            cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking);
-            cudaGraph_t g = nullptr;
-            bool ok = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
-            if (ok) {
-                for (int i = 0; i < kGraphSteps; ++i) launch_substep(s, dt, dt_d, cs);
-                ok = cudaStreamEndCapture(cs, &g) == cudaSuccess && g;
-            }
-            if (ok) ok = cudaGraphInstantiate(&m->graph, g, 0) == cudaSuccess;
-            if (g) cudaGraphDestroy(g);
-            cudaStreamDestroy(cs);
-            if (!ok) { cudaGetLastError(); m->graph = nullptr; }
-            m->graph_valid = ok;
-            m->graph_dt = dt_d;
-        }
-        if (m->graph_valid) {
-            while (n_substeps - done >= kGraphSteps) {
-                if (m->steps_since_order >= kReorderEvery && mpm_build_cell_order(m, st)) return 1;
-                if (cudaGraphLaunch(m->graph, st) != cudaSuccess) { m->error = "cudaGraphLaunch failed"; return 1; }
-                done += kGraphSteps;
-                m->launches += 4 * kGraphSteps;
-                m->steps_since_order += kGraphSteps;
-            }
-        }
-    }
-    for (; done < n_substeps; ++done) { launch_substep(s, dt, dt_d, st); ++m->steps_since_order; m->launches += 4; }
-    const cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) { m->error = std::string("kernel launch failed: ") + cudaGetErrorString(e); return 1; }
-    return 0;
+    return mpm_step_fused(m, n_substeps, dt_d, st);
 }
 
 #define PIXIE_SIMPLE_LAUNCH(kernel)                                                         \
@@ -1169,51 +701,14 @@ int mpm_select_cylinder(Mpm* m, const float* point, const float* normal, float h
                                                               make_float3(normal[0], normal[1], normal[2]), hh, radius, mask);
     return cudaGetLastError() != cudaSuccess;
 }
-// ---- spatially sharded runs (BASELINE config 5): the caller owns the {mv,m} grid, exchanges ghost planes between
-//      scatter and finish, and migrates particles by shrinking / growing the live prefix of the bound arrays.
-int mpm_bind_grid(Mpm* m, void* mv4) {
-    if (switch_to_direct(m)) return 1;
-    m->grid_mv = reinterpret_cast<float4*>(mv4);            // the handle's own buffer (xbuf) stays allocated, unused
-    m->grid_borrowed = true;
-    m->graph_valid = false;
-    return 0;
-}
-int mpm_set_slab(Mpm* m, int x_begin, int x_end) {
-    if (x_begin < 0 || x_end > m->n_grid || x_begin >= x_end) { m->error = "bad slab range"; return 1; }
-    if (switch_to_direct(m)) return 1;
-    m->x_begin = x_begin; m->x_end = x_end;
-    m->graph_valid = false;
-    return 0;
-}
 int mpm_set_active_count(Mpm* m, int n_active) {
     if (n_active < 0 || n_active > m->n) { m->error = "active count exceeds the bound capacity"; return 1; }
     if (mpm_sync(m, 0)) return 1;          // results of the old live prefix go back first; the next step re-reads the arrays
     m->n_active = n_active;
-    m->order_valid = false;       // the order lists exactly the live prefix
     m->graph_valid = false;
     return 0;
 }
-int mpm_substep_scatter(Mpm* m, double dt_d, cudaStream_t st) {
-    if (switch_to_direct(m)) return 1;
-    if (check_bound(m)) return 1;
-    const DevState s = make_state(m);
-    if (s.n > 0) {
-        const int B = particle_block();
-        mpm_stress_kernel<<<(s.n + B - 1) / B, B, 0, st>>>(s, (float)dt_d);
-        mpm_scatter_kernel<1><<<(s.n + B - 1) / B, B, 0, st>>>(s, (float)dt_d);
-    }
-    return cudaGetLastError() != cudaSuccess;
-}
-int mpm_substep_finish(Mpm* m, double dt_d, cudaStream_t st) {
-    if (switch_to_direct(m)) return 1;
-    if (check_bound(m)) return 1;
-    const DevState s = make_state(m);
-    const size_t nodes = (size_t)(s.x_end - s.x_begin) * s.n_grid * s.n_grid;
-    mpm_grid_kernel<<<(unsigned)((nodes + 255) / 256), 256, 0, st>>>(s, (float)dt_d);
-    mpm_g2p_kernel<<<(std::max(s.n, 1) + particle_block() - 1) / particle_block(), particle_block(), 0, st>>>(s, (float)dt_d, dt_d);
-    return cudaGetLastError() != cudaSuccess;
-}
-// ---- slab mode of the fused path (BASELINE config 5). The exchange buffer [SlabFlags][grid_mv] of each handle is made
+// ---- slab mode (BASELINE config 5, no reference counterpart: the reference hard-wires "cuda:0", gs_simulation.py:441). The exchange buffer [SlabFlags][grid_mv] of each handle is made
 //      visible to its x-neighbours (cudaIpc between processes, plain pointers inside one process); scatter, overlap
 //      exchange and grid update then chain on the device with flag handshakes, no host in the loop.
 int mpm_exchange_buffer(Mpm* m, void** base, size_t* bytes) {
@@ -1222,7 +717,6 @@ int mpm_exchange_buffer(Mpm* m, void** base, size_t* bytes) {
     return 0;
 }
 int mpm_slab_attach(Mpm* m, int x0, int x1, int slack, const void* left_xbuf, const void* right_xbuf) {
-    if (!m->fused) { m->error = "slab_attach needs the default (fused) path"; return 1; }
     if (x0 < 0 || x1 > m->n_grid || x0 >= x1 || slack < 0) { m->error = "bad slab range"; return 1; }
     if ((left_xbuf || right_xbuf) && (x1 - x0) < 2 + 2 * slack) { m->error = "slab narrower than 2 + 2*slack planes"; return 1; }
     if (mpm_sync(m, 0)) return 1;
@@ -1256,6 +750,7 @@ int mpm_slab_phase(Mpm* m, int phase, double dt_d, cudaStream_t st) {
         if (!m->internal_valid) { if (fused_gather_from_user(m, st)) return 1; m->g2p_pending = false; }
         else if (m->steps_since_sort >= kResortEvery && fused_resort(m, st)) return 1;
         fused_launch(m, m->g2p_pending, true, true, dt, st);
+        publish_scatter(m, st);
         m->g2p_pending = false;
     } else if (phase == 1) {
         halo_launch(m, st);

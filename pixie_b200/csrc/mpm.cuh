@@ -25,11 +25,7 @@ int mpm_select_box(Mpm* m, const float* point, const float* size, int* mask, cud
 int mpm_select_cylinder(Mpm* m, const float* point, const float* normal, float hh, float radius, int* mask, cudaStream_t st);
 int mpm_grid_ptrs(Mpm* m, float** mv4, float** v4);
 int mpm_sync(Mpm* m, cudaStream_t st);
-int mpm_bind_grid(Mpm* m, void* mv4);
-int mpm_set_slab(Mpm* m, int x_begin, int x_end);
 int mpm_set_active_count(Mpm* m, int n_active);
-int mpm_substep_scatter(Mpm* m, double dt, cudaStream_t st);
-int mpm_substep_finish(Mpm* m, double dt, cudaStream_t st);
 long long mpm_launch_count(Mpm* m);
 int mpm_exchange_buffer(Mpm* m, void** base, size_t* bytes);
 int mpm_slab_attach(Mpm* m, int x0, int x1, int slack, const void* left_xbuf, const void* right_xbuf);

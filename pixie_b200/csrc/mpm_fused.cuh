@@ -111,7 +111,7 @@ __device__ __forceinline__ void gather27(const float4* __restrict__ gv, int n, c
             for (int k = 0; k < 3; ++k) {
                 float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
                 bool ok = true;
-                if (CHECK) ok = (unsigned)(ax.b + i) < (unsigned)n && (unsigned)(ay.b + j) < (unsigned)n && (unsigned)(az.b + k) < (unsigned)n;
+                if (CHECK) ok = (unsigned)ax.b + (unsigned)i < (unsigned)n && (unsigned)ay.b + (unsigned)j < (unsigned)n && (unsigned)az.b + (unsigned)k < (unsigned)n;
                 if (ok) g = __ldg(gv + (base + ((long long)i * n + j) * n + k));
                 const F3 gg = f3(g.x, g.y, g.z);
                 a = fma3(wz[k], gg, a);
@@ -278,7 +278,8 @@ mpm_fused_kernel(const __grid_constant__ FusedState s, const float dt) {
         for (int k = 0; k < 9; ++k) F.m[k] = f[(FS_F + k) * cap + p];
         const AxisW ax = axis_weights(px * s.inv_dx), ay = axis_weights(py * s.inv_dx), az = axis_weights(pz * s.inv_dx);
         F3 v, Bx, By, Bz, Gx, Gy, Gz;
-        const bool inside = ax.b >= 0 && ay.b >= 0 && az.b >= 0 && ax.b + 2 < n && ay.b + 2 < n && az.b + 2 < n;
+        const bool inside = ax.b >= 0 && ay.b >= 0 && az.b >= 0 && ax.b < n - 2 && ay.b < n - 2 && az.b < n - 2;   // (no b + 2: a blown-up
+                                                                                                                  // position converts to INT_MAX)
         if (inside) gather27<false>(s.grid_v, n, ax, ay, az, v, Bx, By, Bz, Gx, Gy, Gz);
         else gather27<true>(s.grid_v, n, ax, ay, az, v, Bx, By, Bz, Gx, Gy, Gz);
         vx = v.x; vy = v.y; vz = v.z;
@@ -373,7 +374,8 @@ mpm_fused_kernel(const __grid_constant__ FusedState s, const float dt) {
 
     // ---------------------------------------------------------------------- p2g (mpm_utils.py:338-394), substep i+1
     const AxisW ax = axis_weights(px * s.inv_dx), ay = axis_weights(py * s.inv_dx), az = axis_weights(pz * s.inv_dx);
-    const bool inside = ax.b >= 0 && ay.b >= 0 && az.b >= 0 && ax.b + 2 < n && ay.b + 2 < n && az.b + 2 < n;
+    const bool inside = ax.b >= 0 && ay.b >= 0 && az.b >= 0 && ax.b < n - 2 && ay.b < n - 2 && az.b < n - 2;   // (no b + 2: a blown-up
+                                                                                                                  // position converts to INT_MAX)
     {   // RPIC damping of C (:374-379)
         const float r = s.rpic_damping;
         if (r < -0.001f) C = m3_zero();
@@ -396,7 +398,7 @@ mpm_fused_kernel(const __grid_constant__ FusedState s, const float dt) {
         if (az.b + 3 > box[5]) atomicMax(s.box + 5, az.b + 3);
     } else if (act) {
         atomicMin(s.box + 0, max(ax.b, 0)); atomicMin(s.box + 1, max(ay.b, 0)); atomicMin(s.box + 2, max(az.b, 0));
-        atomicMax(s.box + 3, min(ax.b + 3, n)); atomicMax(s.box + 4, min(ay.b + 3, n)); atomicMax(s.box + 5, min(az.b + 3, n));
+        atomicMax(s.box + 3, min(max(ax.b, 0), n - 3) + 3); atomicMax(s.box + 4, min(max(ay.b, 0), n - 3) + 3); atomicMax(s.box + 5, min(max(az.b, 0), n - 3) + 3);
     }
 
     // runs of equal base cell among consecutive lanes, chopped at 2^AGG lanes
@@ -456,7 +458,7 @@ mpm_fused_kernel(const __grid_constant__ FusedState s, const float dt) {
                 float a0 = val.x, a1 = val.y, a2 = val.z, a3 = Tm * wza[k];
                 a0 = segsum(a0); a1 = segsum(a1); a2 = segsum(a2); a3 = segsum(a3);
                 bool ok = head && contrib;
-                if (!inside) ok = ok && (unsigned)(ax.b + i) < (unsigned)n && (unsigned)(ay.b + j) < (unsigned)n && (unsigned)(az.b + k) < (unsigned)n;
+                if (!inside) ok = ok && (unsigned)ax.b + (unsigned)i < (unsigned)n && (unsigned)ay.b + (unsigned)j < (unsigned)n && (unsigned)az.b + (unsigned)k < (unsigned)n;
                 ptx::red_add_v4_if(ok, gbase + 4 * (nbase + ((long long)i * n + j) * n + k), a0, a1, a2, a3);
             }
         }
@@ -503,6 +505,17 @@ __device__ __forceinline__ bool wait_peer_flag(const int* flag, int target, int*
     return ok;
 }
 
+// One thread raises a flag of this rank to the current substep (stream order: everything the previous kernel wrote is
+// complete). Kept out of the halo / grid kernels so that a single-process driver can publish for ALL slabs before any of them waits.
+__global__ void mpm_publish_kernel(SlabFlags* mine, int which) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        __threadfence_system();
+        st_release_sys(which == 0 ? &mine->scatter_done : &mine->halo_done, mine->step);
+    }
+}
+
 struct HaloArgs {
     SlabFlags* mine;
     const SlabFlags* peer[2];       // left, right neighbour (nullptr at the domain ends)
@@ -521,7 +534,6 @@ mpm_halo_kernel(const HaloArgs a) {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");          // this rank's scatter of the substep is complete
     const int k = a.mine->step;
-    if (blockIdx.x == 0 && threadIdx.x == 0) { __threadfence_system(); st_release_sys(&a.mine->scatter_done, k); }
     const int n = a.n_grid;
     const int ly = a.box[1], lz = a.box[2], hy = a.box[4], hz = a.box[5];
     const int ey = hy - ly, ez = hz - lz;
@@ -567,7 +579,6 @@ mpm_gridbox_kernel(const GridBoxArgs s, const float dt, const double dt_d) {
     asm volatile("griddepcontrol.wait;" ::: "memory");
     if (s.mine) {
         const int k = s.mine->step;
-        if (blockIdx.x == 0 && threadIdx.x == 0) { __threadfence_system(); st_release_sys(&s.mine->halo_done, k); }
         for (int side = 0; side < 2; ++side)
             if (s.peer[side] && !wait_peer_flag(&s.peer[side]->halo_done, k, &s.mine->error)) return;
     }
@@ -690,7 +701,7 @@ __global__ void fs_box_kernel(const float* __restrict__ x, long long stride_comp
         for (int a = 0; a < 3; ++a) {
             const AxisW w = axis_weights(x[a * stride_comp + p * stride_part] * inv_dx);
             lo[a] = min(lo[a], max(w.b, 0));
-            hi[a] = max(hi[a], min(w.b + 3, n_grid));
+            hi[a] = max(hi[a], min(max(w.b, 0), n_grid - 3) + 3);
         }
     }
 #pragma unroll

@@ -1,5 +1,5 @@
-"""MPM timing A/B on the GPU box (BASELINE config 3: 100k particles, 64^3 grid): fused path with each scatter
-aggregation depth, and the direct four-kernel path. Usage: python scripts/gpu_mpm_perf.py [substeps]"""
+"""MPM timing A/B on the GPU box (BASELINE config 3: 100k particles, 64^3 grid): the default path with each scatter
+aggregation depth (the round-1 four-kernel path it replaced measured 46.6 us on the same box, profiles/r02_mpm_fused_first_perf.log). Usage: python scripts/gpu_mpm_perf.py [substeps]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -62,5 +62,3 @@ if __name__ == "__main__":
     if mode == "full":
         time_it("fused, sand", steps, materials=(2,))
         time_it("fused, 1M / 128^3", 200, n=1_000_000, ng=128)
-        os.environ["PIXIE_MPM_DIRECT"] = "1"
-        time_it("direct (r01 kernels)", steps)

@@ -15,13 +15,8 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
-def _pair(n, ng, materials, seed, prec="f32", bcs=True, g=(0.0, 0.0, -9.8), damping=0.9999, moving=True, direct=False):
+def _pair(n, ng, materials, seed, prec="f32", bcs=True, g=(0.0, 0.0, -9.8), damping=0.9999, moving=True):
     from pixie_b200.mpm_solver_warp import MPM_Simulator_WARP
-    # the solver picks its path when the handle is created
-    if direct:
-        os.environ["PIXIE_MPM_DIRECT"] = "1"      # four-kernel path on the caller's arrays (what slab-decomposed runs use)
-    else:
-        os.environ.pop("PIXIE_MPM_DIRECT", None)
     sc = R.synthetic_scene(n, ng, seed=seed, materials=materials)
     s = MPM_Simulator_WARP(10)
     s.load_initial_data_from_torch(torch.from_numpy(sc["x"]).to(DEV), torch.from_numpy(sc["vol"]).to(DEV), None, n_grid=ng, grid_lim=2.0)
@@ -69,10 +64,9 @@ def _err(s, o, fid):
     return np.abs(a - o.get(fid).reshape(s.n_particles, -1)).max()
 
 
-@pytest.mark.parametrize("direct", [False, True], ids=["fused", "direct"])
 @pytest.mark.parametrize("materials", [(0,), (2,), (1,), (5,), (3,), (0, 1, 2, 3, 4, 5, 6)])
-def test_rollout_matches_fp32_oracle(built_lib, cuda_dev, materials, direct):
-    s, o, _ = _pair(5000, 32, materials, seed=3, direct=direct)
+def test_rollout_matches_fp32_oracle(built_lib, cuda_dev, materials):
+    s, o, _ = _pair(5000, 32, materials, seed=3)
     s.p2g2p(0, 1e-4); o.step(1, 1e-4)
     assert _err(s, o, "X") < 1e-7 and _err(s, o, "V") < 1e-5
     s.p2g2p_n(199, 1e-4); o.step(199, 1e-4)
@@ -145,11 +139,10 @@ def test_conservation_at_full_size(built_lib, cuda_dev):
     assert np.isfinite(x).all() and x.min() > 0.5 and x.max() < 1.5
 
 
-@pytest.mark.parametrize("direct", [False, True], ids=["fused", "direct"])
-def test_drift_vs_fp64_oracle(built_lib, cuda_dev, direct):
+def test_drift_vs_fp64_oracle(built_lib, cuda_dev):
     """Position drift against the fp64 oracle over a rollout, next to the fp32-oracle noise floor."""
     # (no moving collider here: the step at which its faces cross a node is precision dependent by design)
-    s, o64, _ = _pair(20_000, 48, (0,), seed=1, prec="f64", moving=False, direct=direct)
+    s, o64, _ = _pair(20_000, 48, (0,), seed=1, prec="f64", moving=False)
     _, o32, _ = _pair(20_000, 48, (0,), seed=1, prec="f32", moving=False)
     s.p2g2p_n(300, 1e-4); o64.step(300, 1e-4); o32.step(300, 1e-4)
     torch.cuda.synchronize()
