@@ -173,7 +173,7 @@ def run_mpm_slab_block(args, rank, world, dev, pk):
     # dt: the scene's stiffest particles (E = 10^6.5, rho = 200) have a wave speed of 126 m/s; with dx = 2/256 the explicit update
     # needs c dt / dx < 1, i.e. dt < 6e-5 (the 64^3 scene of configs[2] runs at 1e-4 with dx = 2/64)
     n, G, lim, dt = args.slab_particles, args.slab_grid, 2.0, 2e-5
-    slack, migrate_every = 2, 25
+    slack, migrate_every, lazy = args.slab_slack, args.slab_migrate_every, args.slab_lazy_trigger
     sc = synthetic_scene(n, G, seed=0, materials=(0,))              # identical on every rank (seeded)
     base = (sc["x"][:, 0].astype(np.float32) * np.float32(G / lim) - np.float32(0.5)).astype(np.int32)
     bounds = balanced_slab_bounds(base, G, world, 2 + 2 * slack) if world > 1 else [(0, G)]
@@ -204,7 +204,7 @@ def run_mpm_slab_block(args, rank, world, dev, pk):
         s.set_velocity_on_cuboid(point=[1.0, 1.0, 0.62], size=[0.51, 0.51, 0.04], velocity=[0, 0, 0])
     if world > 1:
         r = SlabRank(FusedSlabBackend(s, m), rank, world, slack=slack, migrate_every=migrate_every,
-                     ids=torch.from_numpy(idx.astype(np.int64)), bounds=bounds[rank])
+                     ids=torch.from_numpy(idx.astype(np.int64)), bounds=bounds[rank], lazy_trigger=lazy if lazy > 0 else None)
         drv = DistSlabDriver(r)
         run = lambda k: drv.run(k, dt)
         active = lambda: r.b.active
@@ -217,12 +217,14 @@ def run_mpm_slab_block(args, rank, world, dev, pk):
     if world > 1:
         dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    checks0, migr0 = (r.checks, r.migrations) if world > 1 else (0, 0)
     e0.record(); run(sub); e1.record()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
     cnt = torch.tensor([float(active())], device=dev, dtype=torch.float64)
+    checks, migrations = (r.checks - checks0, r.migrations - migr0) if world > 1 else (0, 0)
     mx = cnt.clone()
     if world > 1:
         r.check_device_error()
@@ -243,6 +245,7 @@ def run_mpm_slab_block(args, rank, world, dev, pk):
     return {"metric": "mpm_particle_steps_per_s", "value": n * sub / (ms * 1e-3), "unit": "particle-steps/s", "us_per_substep": ms / sub * 1e3,
             "scaling": "strong", "substeps": sub, "particles": n, "grid": G, "particles_after": int(cnt.item()),
             "state_finite_and_in_bounds": bool(fin.item() > 0), "dt": dt, "max_particles_per_rank": int(mx.item()), "slab_bounds": bounds, "slack_planes": slack, "migrate_every": migrate_every,
+            "lazy_trigger_planes": lazy, "migration_checks_in_timed_region": checks, "migrations_in_timed_region": migrations,
             "exchange": ("none (undivided scene)" if world == 1 else
                          "device-side: halo kernel reads the neighbour's partial sums over NVLink (cudaIpc-mapped grids, flag handshake); "
                          "migration over NCCL send/recv"),
@@ -552,6 +555,10 @@ def main():
     ap.add_argument("--slab-particles", type=int, default=1_000_000)
     ap.add_argument("--slab-grid", type=int, default=256)
     ap.add_argument("--slab-substeps", type=int, default=200)
+    ap.add_argument("--slab-slack", type=int, default=2, help="planes a particle may drift out of its slab between two migrations")
+    ap.add_argument("--slab-migrate-every", type=int, default=25, help="substeps between two migration check points")
+    ap.add_argument("--slab-lazy-trigger", type=int, default=2,
+                    help="migrate only once a particle is this many planes outside its slab (0: migrate at every check point)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -244,6 +244,9 @@ int pixie_mpm_exchange_buffer(pixie_mpm_t h, void** base, size_t* bytes);
 int pixie_mpm_slab_attach(pixie_mpm_t h, int x0, int x1, int slack, const void* left_xbuf, const void* right_xbuf);
 int pixie_mpm_slab_phase(pixie_mpm_t h, int phase, double dt, void* stream);
 int pixie_mpm_slab_error(pixie_mpm_t h, int* flag);
+/* Migration check without a write-back: the number of planes by which the farthest live particle's stencil base lies
+ * outside [x0, x1) (towards a side that has a neighbour) is max-ed into the DEVICE int *d_out, which the caller zeroes. */
+int pixie_mpm_slab_excursion(pixie_mpm_t h, int* d_out, void* stream);
 /* cudaIpc plumbing for the exchange buffers (64-byte opaque handles, exchanged by the caller, e.g. over torch.distributed). */
 int pixie_ipc_export(const void* dev_ptr, unsigned char handle[64]);
 int pixie_ipc_open(const unsigned char handle[64], void** dev_ptr);

@@ -98,6 +98,7 @@ _SIGNATURES = {
     "pixie_mpm_slab_attach": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "pixie_mpm_slab_phase": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_void_p]),
     "pixie_mpm_slab_error": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
+    "pixie_mpm_slab_excursion": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "pixie_ipc_export": (C.c_int, [C.c_void_p, C.c_char_p]),
     "pixie_ipc_open": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
     "pixie_ipc_close": (C.c_int, [C.c_void_p]),

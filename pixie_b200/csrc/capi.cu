@@ -178,6 +178,7 @@ int pixie_mpm_slab_attach(pixie_mpm_t h, int x0, int x1, int slack, const void* 
 }
 int pixie_mpm_slab_phase(pixie_mpm_t h, int phase, double dt, void* s) { MPM_CALL(pixie::mpm_slab_phase(h->m, phase, dt, (cudaStream_t)s)); }
 int pixie_mpm_slab_error(pixie_mpm_t h, int* flag) { MPM_CALL(pixie::mpm_slab_error(h->m, flag)); }
+int pixie_mpm_slab_excursion(pixie_mpm_t h, int* d_out, void* s) { MPM_CALL(pixie::mpm_slab_excursion(h->m, d_out, (cudaStream_t)s)); }
 int pixie_ipc_export(const void* dev_ptr, unsigned char handle[64]) {
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t size");
     cudaIpcMemHandle_t hd;

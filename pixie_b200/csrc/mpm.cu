@@ -762,6 +762,26 @@ int mpm_slab_phase(Mpm* m, int phase, double dt_d, cudaStream_t st) {
     } else { m->error = "bad phase"; return 1; }
     return cudaGetLastError() != cudaSuccess;
 }
+// Planes by which the farthest live particle's stencil base lies outside this slab's [x0, x1) (sides without a neighbour do
+// not count), max-ed into the device int `d_out` (the caller zeroes it). Reads the sorted state when it is current, so a
+// migration check costs one small kernel instead of a write-back of every field.
+int mpm_slab_excursion(Mpm* m, int* d_out, cudaStream_t st) {
+    if (!m->slab) { m->error = "not in slab mode"; return 1; }
+    if (m->n_active <= 0) return 0;
+    const float inv_dx = (float)((double)m->n_grid / (double)m->grid_lim);
+    const int lo = m->peer_xbuf[0] ? m->slab_x0 : -(1 << 29);
+    const int hi = m->peer_xbuf[1] ? m->slab_x1 : (1 << 29);
+    const bool sorted = m->internal_valid && m->fs[0].f;
+    if (sorted && m->g2p_pending) {                    // phase-driven runs: positions of the last substep first
+        fused_launch(m, true, false, true, m->slab_dt, st);
+        m->g2p_pending = false;
+    }
+    const float* x = sorted ? m->fs[0].f + (size_t)FS_X * m->cap : reinterpret_cast<const float*>(m->fields[PIXIE_MPM_X]);
+    if (!x) { m->error = "positions not bound"; return 1; }
+    fs_excursion_kernel<<<148, 256, 0, st>>>(x, sorted ? 1 : 3, m->n_active, inv_dx, lo, hi, d_out);
+    m->launches += 1;
+    return cudaGetLastError() != cudaSuccess;
+}
 int mpm_slab_error(Mpm* m, int* flag) {
     SlabFlags f{};
     if (cudaMemcpy(&f, m->xbuf, sizeof(f), cudaMemcpyDeviceToHost) != cudaSuccess) return 1;

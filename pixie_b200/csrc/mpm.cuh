@@ -31,5 +31,6 @@ int mpm_exchange_buffer(Mpm* m, void** base, size_t* bytes);
 int mpm_slab_attach(Mpm* m, int x0, int x1, int slack, const void* left_xbuf, const void* right_xbuf);
 int mpm_slab_phase(Mpm* m, int phase, double dt, cudaStream_t st);
 int mpm_slab_error(Mpm* m, int* flag);
+int mpm_slab_excursion(Mpm* m, int* d_out, cudaStream_t st);
 const std::string& mpm_error(Mpm* m);
 }  // namespace pixie

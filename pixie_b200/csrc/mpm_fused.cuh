@@ -714,6 +714,18 @@ __global__ void fs_box_kernel(const float* __restrict__ x, long long stride_comp
     }
 }
 
+// slab runs: how many planes the farthest particle's stencil base lies outside [lo, hi) (0 = all inside); `out` is max-ed into
+__global__ void fs_excursion_kernel(const float* __restrict__ x, long long stride_part, int n, float inv_dx, int lo, int hi,
+                                    int* __restrict__ out) {
+    int e = 0;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+        const int b = axis_weights(x[p * stride_part] * inv_dx).b;
+        e = max(e, max(lo - b, b - (hi - 1)));
+    }
+    for (int o = 16; o > 0; o >>= 1) e = max(e, __shfl_xor_sync(0xffffffffu, e, o));
+    if ((threadIdx.x & 31) == 0 && e > 0) atomicMax(out, e);
+}
+
 struct FsUser {      // the caller's arrays (array-of-structs, original order)
     float *x, *v, *C, *F, *Ft, *stress, *mass, *vol, *mu, *lam, *bulk, *ys, *cov;
     int *material, *selection;

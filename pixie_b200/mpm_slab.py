@@ -122,6 +122,14 @@ class FusedSlabBackend:
             self._check(self.lib.pixie_mpm_slab_error(self.solver._handle, C.byref(flag)))
         return flag.value
 
+    def excursion(self) -> torch.Tensor:
+        """int32[1] on the device: planes by which the farthest particle's stencil base lies outside this slab (one small kernel
+        over the sorted positions; no write-back of the particle fields, no host sync)."""
+        out = torch.zeros(1, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.pixie_mpm_slab_excursion(self.solver._handle, C.c_void_p(out.data_ptr()), self._stream()))
+        return out
+
     # -- particles
     @property
     def active(self) -> int:
@@ -192,8 +200,15 @@ class SlabRank:
     """Phase methods of one rank; a driver (`DistSlabDriver` or `LocalSlabCluster`) sequences them."""
 
     def __init__(self, backend, rank: int, world: int, slack: int = 1, migrate_every: int = 8, ids: Optional[torch.Tensor] = None,
-                 bounds: Optional[Tuple[int, int]] = None):
+                 bounds: Optional[Tuple[int, int]] = None, lazy_trigger: Optional[int] = None):
+        """`lazy_trigger`: None migrates at every check point (every `migrate_every` substeps). An integer t (1 <= t <= slack)
+        migrates only once some particle of SOME rank has its stencil base t or more planes outside its slab; until then
+        the slack planes absorb the movers and a check point costs one small kernel + a 4-byte all-reduce."""
         self.b, self.rank, self.world, self.slack, self.migrate_every = backend, rank, world, slack, migrate_every
+        if lazy_trigger is not None and not (1 <= lazy_trigger <= max(1, slack)):
+            raise ValueError("lazy_trigger must lie in [1, slack]")
+        self.lazy_trigger = lazy_trigger
+        self.checks = self.migrations = 0
         n = backend.n_grid
         self.x0, self.x1 = bounds if bounds is not None else slab_bounds(n, world, rank)
         if world > 1 and (self.x1 - self.x0) < 2 + 2 * slack:
@@ -238,6 +253,30 @@ class SlabRank:
 
     def due_for_migration(self) -> bool:
         return self.world > 1 and self.steps % self.migrate_every == 0
+
+    def excursion(self) -> torch.Tensor:
+        """int32[1]: planes by which this rank's farthest particle base lies outside [x0, x1) towards a neighbour."""
+        if hasattr(self.b, "excursion"):
+            return self.b.excursion()
+        x = self.b.get("X")[:, 0]
+        base = (x.to(torch.float32) * torch.tensor(self.b.inv_dx, dtype=torch.float32, device=x.device) - 0.5).to(torch.int32)
+        e = torch.zeros(1, dtype=torch.int32, device=x.device)
+        if base.numel():
+            if self.has_left:
+                e = torch.maximum(e, (self.x0 - base.min()).to(torch.int32).view(1))
+            if self.has_right:
+                e = torch.maximum(e, (base.max() - (self.x1 - 1)).to(torch.int32).view(1))
+        return e
+
+    def migration_needed(self, global_excursion: int) -> bool:
+        """Decision at a check point from the max excursion over ALL ranks (every rank must take the same branch)."""
+        self.checks += 1
+        if global_excursion > self.slack:
+            raise RuntimeError(f"slab rank {self.rank}: a particle drifted more than slack={self.slack} planes out of its slab "
+                               f"between two migration checks; lower migrate_every or raise slack")
+        need = self.lazy_trigger is None or global_excursion >= self.lazy_trigger
+        self.migrations += int(need)
+        return need
 
     # -- migration phases
     def check_device_error(self):
@@ -315,12 +354,19 @@ class LocalSlabCluster:
                 r.accumulate(from_left, from_right)
         for r in R:
             r.finish(dt)
-        if R[0].due_for_migration():
+        if R[0].due_for_migration() and self._migration_needed():
             parts = [r.migrate_collect() for r in R]
             for i, r in enumerate(R):
                 from_left = parts[i - 1][2] if r.has_left else None
                 from_right = parts[i + 1][1] if r.has_right else None
                 r.migrate_apply(parts[i][0], from_left, from_right)
+
+    def _migration_needed(self) -> bool:
+        R = self.ranks
+        if R[0].lazy_trigger is None:
+            return all([r.migration_needed(0) for r in R])
+        e = max(int(r.excursion().item()) for r in R)
+        return all([r.migration_needed(e) for r in R])
 
     def gather(self, name: str) -> torch.Tensor:
         """Field `name` of every particle, ordered by global id."""
@@ -366,8 +412,18 @@ class DistSlabDriver:
             if r.due_for_migration():
                 self._migrate()
 
+    def _migration_needed(self) -> bool:
+        r = self.r
+        if r.lazy_trigger is None:
+            return r.migration_needed(0)
+        e = r.excursion()
+        self.dist.all_reduce(e, op=self.dist.ReduceOp.MAX, group=self.group)
+        return r.migration_needed(int(e.item()))
+
     def _migrate(self):
         r = self.r
+        if not self._migration_needed():
+            return
         stay, go_left, go_right = r.migrate_collect()
         from_left, from_right = self._swap_var(go_left if r.has_left else None, go_right if r.has_right else None)
         r.migrate_apply(stay, from_left, from_right)
@@ -418,9 +474,7 @@ class DistSlabDriver:
         r.accumulate(from_left, from_right)
         r.finish(dt)
         if r.due_for_migration():
-            stay, go_left, go_right = r.migrate_collect()
-            from_left, from_right = self._swap_var(go_left if r.has_left else None, go_right if r.has_right else None)
-            r.migrate_apply(stay, from_left, from_right)
+            self._migrate()
 
     def gather(self, name: str, dst: int = 0) -> Optional[torch.Tensor]:
         """Field `name` of every particle ordered by global id, on rank `dst` (None elsewhere)."""

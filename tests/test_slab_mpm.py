@@ -27,13 +27,14 @@ def _owned(fields, world, rank):
     return np.where((base >= lo) & (base < hi))[0]
 
 
-def _oracle_rank(fields, world, rank, migrate_every):
+def _oracle_rank(fields, world, rank, migrate_every, slack=1, lazy_trigger=None):
     from slab_backends import OracleSlabBackend, load_scene
     idx = _owned(fields, world, rank)
     b = OracleSlabBackend(G, LIM, N, "f64")
     load_scene(b.sim, fields, idx)
     b._active = len(idx)
-    return SlabRank(b, rank, world, slack=1, migrate_every=migrate_every, ids=torch.from_numpy(idx.astype(np.int64)))
+    return SlabRank(b, rank, world, slack=slack, migrate_every=migrate_every, ids=torch.from_numpy(idx.astype(np.int64)),
+                    lazy_trigger=lazy_trigger)
 
 
 def _reference(fields, steps):
@@ -63,6 +64,27 @@ def test_local_cluster_matches_single_domain(world, migrate_every):
         assert np.abs(got - want).max() < 1e-11, name    # f64: only the summation order at shared nodes differs
 
 
+def test_lazy_migration_matches_single_domain_and_migrates_less():
+    """Check points every 2 substeps, but particles only move once one of them is a whole plane past the first slack plane."""
+    from slab_backends import make_scene
+    fields = make_scene(N, G, LIM)
+    world, steps = 2, 80
+    ranks = [_oracle_rank(fields, world, r, 2, slack=2, lazy_trigger=2) for r in range(world)]
+    before = [r.b.active for r in ranks]
+    cl = LocalSlabCluster(ranks)
+    for _ in range(steps):
+        cl.substep(DT)
+    ref = _reference(fields, steps)
+    assert sum(r.b.active for r in ranks) == N
+    assert ranks[0].checks == steps // 2 and 1 <= ranks[0].migrations < ranks[0].checks // 2
+    assert [r.b.active for r in ranks] != before
+    for name in ("X", "V", "F_TRIAL"):
+        got = cl.gather(name).numpy().reshape(N, -1)
+        assert np.abs(got - np.asarray(ref.get(name)).reshape(N, -1)).max() < 1e-11, name
+    with pytest.raises(ValueError):
+        _oracle_rank(fields, world, 0, 2, slack=2, lazy_trigger=3)
+
+
 def test_slab_too_narrow_is_rejected():
     from slab_backends import OracleSlabBackend
     b = OracleSlabBackend(8, 1.0, 4, "f64")
@@ -78,7 +100,7 @@ def _free_port():
     return p
 
 
-def _gloo_worker(rank, world, port, steps, q):
+def _gloo_worker(rank, world, port, steps, q, lazy=False):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OMP_NUM_THREADS="1")
@@ -86,7 +108,7 @@ def _gloo_worker(rank, world, port, steps, q):
     from slab_backends import make_scene
     dist.init_process_group("gloo", rank=rank, world_size=world)
     fields = make_scene(N, G, LIM)
-    drv = DistSlabDriver(_oracle_rank(fields, world, rank, 4))
+    drv = DistSlabDriver(_oracle_rank(fields, world, rank, 4, slack=2, lazy_trigger=2) if lazy else _oracle_rank(fields, world, rank, 4))
     for _ in range(steps):
         drv.substep(DT)
     x = drv.gather("X")
@@ -96,13 +118,14 @@ def _gloo_worker(rank, world, port, steps, q):
     dist.destroy_process_group()
 
 
-def test_gloo_world2_matches_single_domain():
+@pytest.mark.parametrize("lazy", [False, True])
+def test_gloo_world2_matches_single_domain(lazy):
     from slab_backends import make_scene
     world, steps = 2, 40
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_gloo_worker, args=(r, world, port, steps, q)) for r in range(world)]
+    procs = [ctx.Process(target=_gloo_worker, args=(r, world, port, steps, q, lazy)) for r in range(world)]
     for p in procs:
         p.start()
     res = {}
@@ -141,7 +164,7 @@ def _cuda_solver(fields, idx, capacity):
     return s
 
 
-def _cuda_cluster(fields, world, migrate_every, bounds=None):
+def _cuda_cluster(fields, world, migrate_every, bounds=None, slack=1, lazy_trigger=None):
     import ctypes as C
     from pixie_b200 import _lib
     from pixie_b200.mpm_slab import FusedSlabBackend
@@ -164,8 +187,9 @@ def _cuda_cluster(fields, world, migrate_every, bounds=None):
             idx = np.where((base >= lo) & (base < hi))[0]
         s = _cuda_solver(fields, idx, N)
         finish_setup(s)
-        ranks.append(SlabRank(FusedSlabBackend(s, len(idx)), r, world, slack=1, migrate_every=migrate_every,
-                              ids=torch.from_numpy(idx.astype(np.int64)), bounds=None if bounds is None else bounds[r]))
+        ranks.append(SlabRank(FusedSlabBackend(s, len(idx)), r, world, slack=slack, migrate_every=migrate_every,
+                              ids=torch.from_numpy(idx.astype(np.int64)), bounds=None if bounds is None else bounds[r],
+                              lazy_trigger=lazy_trigger))
     return ranks, finish_setup
 
 
@@ -200,6 +224,33 @@ def test_cuda_slabs_match_single_domain_cuda(world, migrate_every):
     assert np.abs(x_slab - x_ref).max() < 5e-5
     ft = cl.gather("F_TRIAL").numpy().reshape(N, 9)
     assert np.abs(ft - np.asarray(ref.get("F_TRIAL")).reshape(N, 9)).max() < 5e-4
+
+
+@pytest.mark.gpu
+def test_cuda_lazy_migration_matches_single_domain():
+    """Migration checks by the excursion kernel (sorted positions, no write-back): same trajectory, fewer migrations."""
+    from slab_backends import make_scene
+    fields = make_scene(N, G, LIM)
+    steps = 80
+    ranks, finish_setup = _cuda_cluster(fields, 2, 2, slack=2, lazy_trigger=2)
+    before = [r.b.active for r in ranks]
+    cl = LocalSlabCluster(ranks)
+    for _ in range(steps):
+        cl.substep(DT)
+    torch.cuda.synchronize()
+    for r in ranks:
+        r.check_device_error()
+    assert ranks[0].checks == steps // 2 and 1 <= ranks[0].migrations < ranks[0].checks // 2
+    assert sum(r.b.active for r in ranks) == N and [r.b.active for r in ranks] != before
+    # the device excursion equals the one computed from the written-back positions
+    for r in ranks:
+        dev_e = int(r.b.excursion().item())
+        x = r.b.get("X")[:, 0]
+        base = (x * torch.tensor(r.b.inv_dx, dtype=torch.float32, device=x.device) - 0.5).to(torch.int32)
+        want = max(0, (r.x0 - int(base.min())) if r.has_left else 0, (int(base.max()) - (r.x1 - 1)) if r.has_right else 0)
+        assert dev_e == want
+    ref = _reference(fields, steps)
+    assert np.abs(cl.gather("X").numpy().reshape(N, 3) - np.asarray(ref.get("X"))).max() < 5e-5
 
 
 @pytest.mark.gpu
