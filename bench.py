@@ -227,7 +227,10 @@ def run_mpm_slab_block(args, rank, world, dev, pk):
     checks, migrations = (r.checks - checks0, r.migrations - migr0) if world > 1 else (0, 0)
     mx = cnt.clone()
     if world > 1:
-        r.check_device_error()
+        derr = torch.tensor([float(r.b.error())], device=dev, dtype=torch.float64)
+        dist.all_reduce(derr, op=dist.ReduceOp.MAX)
+        if derr.item() != 0:             # same value on every rank: all of them leave together
+            raise RuntimeError(f"slab exchange reported device error {int(derr.item())} (1: neighbour timeout, 2: drift beyond slack)")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
@@ -502,7 +505,11 @@ def run_ours(args, emit):
     if not args.skip_slab:
         del solver
         torch.cuda.empty_cache()
-        slab = run_mpm_slab_block(args, rank, world, dev, pk)
+        try:
+            slab = run_mpm_slab_block(args, rank, world, dev, pk)
+        except Exception as e:           # reported, not fatal: the headline line must still be printed
+            slab = {"error": f"{type(e).__name__}: {e}"}
+            print(f"[bench] mpm_slab block failed on rank {rank}: {slab['error']}", file=sys.stderr)
 
     if world > 1:
         dist.barrier()

@@ -413,12 +413,25 @@ class DistSlabDriver:
                 self._migrate()
 
     def _migration_needed(self) -> bool:
+        """One 8-byte all-reduce per check point: [max excursion, max device error flag]. Every rank sees the same values,
+        so a failure (a neighbour that never showed up, a particle beyond the slack planes) raises on ALL ranks instead of
+        leaving the others waiting in a collective."""
         r = self.r
-        if r.lazy_trigger is None:
-            return r.migration_needed(0)
-        e = r.excursion()
-        self.dist.all_reduce(e, op=self.dist.ReduceOp.MAX, group=self.group)
-        return r.migration_needed(int(e.item()))
+        e = r.excursion() if r.lazy_trigger is not None else None
+        err = r.b.error() if hasattr(r.b, "error") else 0
+        dev = e.device if e is not None else torch.device(getattr(r.b, "device", "cpu"))
+        both = torch.zeros(2, dtype=torch.int32, device=dev)
+        if e is not None:
+            both[0:1] = e
+        both[1] = err
+        self.dist.all_reduce(both, op=self.dist.ReduceOp.MAX, group=self.group)
+        ge, gerr = (int(v) for v in both.tolist())
+        if gerr == 1:
+            raise RuntimeError(f"slab rank {r.rank}: a rank waited for a neighbour that did not reach the exchange (flag timeout)")
+        if gerr == 2:
+            raise RuntimeError(f"slab rank {r.rank}: a particle drifted more than slack={r.slack} planes out of its slab between "
+                               f"two migrations; lower migrate_every or raise slack")
+        return r.migration_needed(ge)
 
     def _migrate(self):
         r = self.r
