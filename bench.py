@@ -238,6 +238,34 @@ def run_mpm_slab_block(args, rank, world, dev, pk):
     fin = torch.tensor([float(np.isfinite(xs).all() and xs.min() > 0.3 and xs.max() < 1.7)], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(fin, op=dist.ReduceOp.MIN)
+    # ---- the decomposed run against the undivided one (same scene, same number of substeps, rank 0's GPU): the device-side
+    #      exchange must reproduce it up to the summation order of the fp32 atomics
+    vs_single = None
+    if world > 1 and not args.skip_slab_parity:
+        total_sub = migrate_every * 2 + sub
+        x_all = drv.gather("X")                                       # rank 0: [n, 3] ordered by global particle id
+        if rank == 0:
+            with contextlib.redirect_stdout(sys.stderr):
+                w = MPM_Simulator_WARP(n, n_grid=G, grid_lim=lim, device=dev)
+                for fid, key in (("X", "x"), ("V", "v"), ("VOL", "vol"), ("DENSITY", "density"), ("E", "E"), ("NU", "nu")):
+                    tt = w._t[fid]
+                    tt.view(n, tt.numel() // n)[:] = torch.as_tensor(np.asarray(sc[key]).reshape(n, -1), dtype=torch.float32, device=dev)
+                w._t["MATERIAL"].view(n, 1)[:] = torch.as_tensor(np.asarray(sc["material"]).reshape(n, 1), dtype=torch.int32, device=dev)
+                ft = w._t["F_TRIAL"]; ft.zero_(); ft[:, 0, 0] = 1; ft[:, 1, 1] = 1; ft[:, 2, 2] = 1
+                w.mpm_model.gravitational_accelaration = (0.0, 0.0, -9.8)
+                w.mpm_model.grid_v_damping_scale = 0.9999
+                w._push_params()
+                _lib.check(lib.pixie_mpm_compute_mass(w._handle, w._stream()))
+                _lib.check(lib.pixie_mpm_compute_mu_lam(w._handle, w._stream()))
+                w.add_bounding_box()
+                w.set_velocity_on_cuboid(point=[1.0, 1.0, 0.62], size=[0.51, 0.51, 0.04], velocity=[0, 0, 0])
+                w.p2g2p_n(total_sub, dt)
+            xw = w.mpm_state.particle_x.numpy().reshape(n, 3).astype(np.float64)
+            moved = float(np.abs(xw - np.asarray(sc["x"], dtype=np.float64).reshape(n, 3)).max())
+            dmax = float(np.abs(x_all.numpy().reshape(n, 3) - xw).max())
+            vs_single = {"max_abs_dx": dmax, "substeps": total_sub, "max_displacement_of_the_run": moved, "tolerance": 1e-4,
+                         "ok": bool(dmax < 1e-4)}
+            del w
     if rank != 0:
         return None
     ms = float(t.item())
@@ -247,7 +275,7 @@ def run_mpm_slab_block(args, rank, world, dev, pk):
     ext = [int(np.floor(sc["x"][:, a].max() * G / lim - 0.5)) + 3 - int(np.floor(sc["x"][:, a].min() * G / lim - 0.5)) + 4 for a in (1, 2)]
     return {"metric": "mpm_particle_steps_per_s", "value": n * sub / (ms * 1e-3), "unit": "particle-steps/s", "us_per_substep": ms / sub * 1e3,
             "scaling": "strong", "substeps": sub, "particles": n, "grid": G, "particles_after": int(cnt.item()),
-            "state_finite_and_in_bounds": bool(fin.item() > 0), "dt": dt, "max_particles_per_rank": int(mx.item()), "slab_bounds": bounds, "slack_planes": slack, "migrate_every": migrate_every,
+            "state_finite_and_in_bounds": bool(fin.item() > 0), "vs_single_domain_run": vs_single, "dt": dt, "max_particles_per_rank": int(mx.item()), "slab_bounds": bounds, "slack_planes": slack, "migrate_every": migrate_every,
             "lazy_trigger_planes": lazy, "migration_checks_in_timed_region": checks, "migrations_in_timed_region": migrations,
             "exchange": ("none (undivided scene)" if world == 1 else
                          "device-side: halo kernel reads the neighbour's partial sums over NVLink (cudaIpc-mapped grids, flag handshake); "
@@ -562,6 +590,7 @@ def main():
     ap.add_argument("--slab-particles", type=int, default=1_000_000)
     ap.add_argument("--slab-grid", type=int, default=256)
     ap.add_argument("--slab-substeps", type=int, default=200)
+    ap.add_argument("--skip-slab-parity", action="store_true", help="skip the decomposed-vs-undivided trajectory check at N > 1")
     ap.add_argument("--slab-slack", type=int, default=2, help="planes a particle may drift out of its slab between two migrations")
     ap.add_argument("--slab-migrate-every", type=int, default=25, help="substeps between two migration check points")
     ap.add_argument("--slab-lazy-trigger", type=int, default=2,

@@ -448,8 +448,9 @@ static void gridbox_launch(Mpm* m, float dt, double dt_d, cudaStream_t st) {
     m->tpar ^= 1;
 }
 
-static void halo_launch(Mpm* m, cudaStream_t st) {
+static void halo_launch(Mpm* m, bool publish_scatter, cudaStream_t st) {
     HaloArgs a{};
+    a.publish_scatter = publish_scatter ? 1 : 0;
     a.mine = reinterpret_cast<SlabFlags*>(m->xbuf);
     a.grid_mv = m->grid_mv; a.box = m->d_box; a.n_grid = m->n_grid;
     for (int sd = 0; sd < 2; ++sd) {
@@ -457,22 +458,17 @@ static void halo_launch(Mpm* m, cudaStream_t st) {
         a.peer_mv[sd] = m->peer_xbuf[sd] ? reinterpret_cast<const float4*>(m->peer_xbuf[sd] + sizeof(SlabFlags)) : nullptr;
         a.total[sd] = m->ov_total[sd]; a.ov_lo[sd] = m->ov_lo[sd]; a.ov_hi[sd] = m->ov_hi[sd];
     }
-    pdl_launch(mpm_halo_kernel, dim3(148), dim3(256), st, a);
-    pdl_launch(mpm_publish_kernel, dim3(1), dim3(32), st, a.mine, 1);          // halo_done: the neighbours may clear what this rank read
-    m->launches += 2;
-}
-static void publish_scatter(Mpm* m, cudaStream_t st) {
-    pdl_launch(mpm_publish_kernel, dim3(1), dim3(32), st, reinterpret_cast<SlabFlags*>(m->xbuf), 0);
+    pdl_launch(mpm_halo_kernel, dim3(148), dim3(256), st, a);          // its last block raises halo_done
     m->launches += 1;
 }
 
 // `count` substeps as: scatter(0) | [halo(0)] | grid(0) | g2p(0)+scatter(1) | ... | grid(count-1) | g2p(count-1)
 static void fused_batch(Mpm* m, int count, float dt, double dt_d, cudaStream_t st) {
-    fused_launch(m, false, true, count == 1 || m->slab, dt, st);
+    fused_launch(m, false, true, count == 1, dt, st);
     for (int i = 0; i < count; ++i) {
-        if (m->slab) { publish_scatter(m, st); halo_launch(m, st); }
+        if (m->slab) halo_launch(m, true, st);
         gridbox_launch(m, dt, dt_d, st);
-        if (i + 1 < count) fused_launch(m, true, true, i + 2 == count || m->slab, dt, st);
+        if (i + 1 < count) fused_launch(m, true, true, i + 2 == count, dt, st);
         else fused_launch(m, true, false, true, dt, st);
     }
 }
@@ -656,6 +652,10 @@ static int check_bound(Mpm* m) {
 int mpm_step(Mpm* m, int n_substeps, double dt_d, cudaStream_t st) {
     if (check_bound(m)) return 1;
     if (n_substeps <= 0) return 0;
+    if (m->g2p_pending && m->internal_valid) {          // phase-driven substeps came first: complete the last one
+        fused_launch(m, true, false, true, m->slab_dt, st);
+        m->g2p_pending = false;
+    }
     return mpm_step_fused(m, n_substeps, dt_d, st);
 }
 
@@ -750,10 +750,11 @@ int mpm_slab_phase(Mpm* m, int phase, double dt_d, cudaStream_t st) {
         if (!m->internal_valid) { if (fused_gather_from_user(m, st)) return 1; m->g2p_pending = false; }
         else if (m->steps_since_sort >= kResortEvery && fused_resort(m, st)) return 1;
         fused_launch(m, m->g2p_pending, true, true, dt, st);
-        publish_scatter(m, st);
+        pdl_launch(mpm_publish_kernel, dim3(1), dim3(32), st, reinterpret_cast<SlabFlags*>(m->xbuf));
+        m->launches += 1;
         m->g2p_pending = false;
     } else if (phase == 1) {
-        halo_launch(m, st);
+        halo_launch(m, false, st);
     } else if (phase == 2) {
         gridbox_launch(m, dt, dt_d, st);
         m->g2p_pending = true; m->slab_dt = dt;

@@ -65,6 +65,15 @@ struct FusedState {
     int base_lo, base_hi;
 };
 
+__device__ __forceinline__ int ld_acquire_sys(const int* p) {
+    int v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(int* p, int v) {
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 struct AxisW { float w0, w1, w2, d0, d1, d2, fx; int b; };   // weights, derivative weights (without inv_dx), offset, base
 
 __device__ __forceinline__ AxisW axis_weights(float g) {
@@ -472,18 +481,11 @@ struct SlabFlags {
     int halo_done;        // substep whose overlap totals this rank has finished reading from its neighbours
     int error;            // 1: a neighbour did not show up in time, 2: a particle drifted beyond the slack planes
     int step;             // this rank's substep counter
-    int pad[60];
+    int halo_blocks;      // blocks of the running halo kernel that are done (the last one raises halo_done)
+    int pad[59];
 };
 static_assert(sizeof(SlabFlags) == 256, "SlabFlags layout");
 
-__device__ __forceinline__ int ld_acquire_sys(const int* p) {
-    int v;
-    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_sys(int* p, int v) {
-    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
 // Thread 0 of the block polls a neighbour's flag until it reaches `target` (bounded: ~1 s), then the block proceeds.
 __device__ __forceinline__ bool wait_peer_flag(const int* flag, int target, int* my_err) {
     __shared__ int ok_s;
@@ -505,14 +507,14 @@ __device__ __forceinline__ bool wait_peer_flag(const int* flag, int target, int*
     return ok;
 }
 
-// One thread raises a flag of this rank to the current substep (stream order: everything the previous kernel wrote is
-// complete). Kept out of the halo / grid kernels so that a single-process driver can publish for ALL slabs before any of them waits.
-__global__ void mpm_publish_kernel(SlabFlags* mine, int which) {
+// Phase API only (a single-process driver sequences the phases of SEVERAL slabs on one stream and must raise every slab's
+// scatter_done before the first halo launch waits): one thread raises the flag after the particle kernel in front of it.
+__global__ void mpm_publish_kernel(SlabFlags* mine) {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         __threadfence_system();
-        st_release_sys(which == 0 ? &mine->scatter_done : &mine->halo_done, mine->step);
+        st_release_sys(&mine->scatter_done, mine->step);
     }
 }
 
@@ -525,6 +527,7 @@ struct HaloArgs {
     const int* box;
     int n_grid;
     int ov_lo[2], ov_hi[2];         // shared plane ranges [lo, hi)
+    int publish_scatter;            // 1: this launch also raises scatter_done (chained runs); 0: a publish launch did (phase API)
 };
 
 // Overlap totals: total = own partial + neighbour's partial on the shared planes, inside this rank's node box (the only
@@ -537,21 +540,61 @@ mpm_halo_kernel(const HaloArgs a) {
     const int n = a.n_grid;
     const int ly = a.box[1], lz = a.box[2], hy = a.box[4], hz = a.box[5];
     const int ey = hy - ly, ez = hz - lz;
+    // the particle kernel in front of this launch has completed (griddepcontrol.wait / stream order): tell the neighbours that
+    // this rank's partial sums of substep k are in place BEFORE waiting for theirs (release at system scope: they read them
+    // over NVLink). The particle kernel itself stays free of fences: its reds remain fire-and-forget.
+    if (a.publish_scatter && blockIdx.x == 0 && threadIdx.x == 0) {
+        __threadfence_system();
+        st_release_sys(&a.mine->scatter_done, k);
+    }
+    // both neighbours' flags are awaited at the same time (two polling threads), then ONE pass covers both overlaps: the
+    // remote reads of the two sides are in flight together
+    __shared__ int ok_s[2];
+    if (threadIdx.x < 64 && (threadIdx.x & 31) == 0) {
+        const int side = threadIdx.x >> 5;
+        int ok = 1;
+        if (a.peer[side]) {
+            ok = 0;
+            for (long long it = 0; it < (1ll << 22); ++it) {
+                if (ld_acquire_sys(&a.peer[side]->scatter_done) >= k) { ok = 1; break; }
+                __nanosleep(100);
+            }
+            if (!ok) atomicExch(&a.mine->error, 1);
+        }
+        ok_s[side] = ok;
+    }
+    __syncthreads();
+    const bool ok = ok_s[0] && ok_s[1];
+    long long cnt[2], off[2] = {0, 0};
+    int lxs[2], exs[2];
 #pragma unroll
     for (int side = 0; side < 2; ++side) {
-        if (!a.peer[side]) continue;
-        if (!wait_peer_flag(&a.peer[side]->scatter_done, k, &a.mine->error)) return;
-        const int lx = max(a.ov_lo[side], a.box[0]), hx = min(a.ov_hi[side], a.box[3]);
-        const int ex = hx - lx;
-        if (ex <= 0 || ey <= 0 || ez <= 0) continue;
-        const long long total = (long long)ex * ey * ez;
-        for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        lxs[side] = max(a.ov_lo[side], a.box[0]);
+        exs[side] = min(a.ov_hi[side], a.box[3]) - lxs[side];
+        cnt[side] = (a.peer[side] && exs[side] > 0 && ey > 0 && ez > 0) ? (long long)exs[side] * ey * ez : 0;
+    }
+    off[1] = cnt[0];
+    const long long total = cnt[0] + cnt[1];
+    if (ok)
+        for (long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; t0 < total; t0 += (long long)gridDim.x * blockDim.x) {
+            const int side = t0 >= off[1] ? 1 : 0;
+            const long long t = t0 - off[side];
             const int iz = (int)(t % ez), iy = (int)((t / ez) % ey), ix = (int)(t / ((long long)ez * ey));
-            const size_t idx = ((size_t)(lx + ix) * n + (ly + iy)) * n + (lz + iz);
+            const size_t idx = ((size_t)(lxs[side] + ix) * n + (ly + iy)) * n + (lz + iz);
             const float4 own = a.grid_mv[idx];
             const float4 oth = a.peer_mv[side][idx];                 // peer memory (NVLink) or the other slab of a test
-            const size_t tix = ((size_t)(lx + ix - a.ov_lo[side]) * n + (ly + iy)) * n + (lz + iz);
+            const size_t tix = ((size_t)(lxs[side] + ix - a.ov_lo[side]) * n + (ly + iy)) * n + (lz + iz);
             a.total[side][tix] = make_float4(own.x + oth.x, own.y + oth.y, own.z + oth.z, own.w + oth.w);
+        }
+    // the last block raises halo_done: the neighbours may now clear what this rank has read
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const int done = atomicAdd(&a.mine->halo_blocks, 1);
+        if (done == (int)gridDim.x - 1) {
+            a.mine->halo_blocks = 0;
+            __threadfence_system();
+            if (ok) st_release_sys(&a.mine->halo_done, k);
         }
     }
 }

@@ -355,11 +355,15 @@ class LocalSlabCluster:
         for r in R:
             r.finish(dt)
         if R[0].due_for_migration() and self._migration_needed():
-            parts = [r.migrate_collect() for r in R]
-            for i, r in enumerate(R):
-                from_left = parts[i - 1][2] if r.has_left else None
-                from_right = parts[i + 1][1] if r.has_right else None
-                r.migrate_apply(parts[i][0], from_left, from_right)
+            self._migrate()
+
+    def _migrate(self):
+        R = self.ranks
+        parts = [r.migrate_collect() for r in R]
+        for i, r in enumerate(R):
+            from_left = parts[i - 1][2] if r.has_left else None
+            from_right = parts[i + 1][1] if r.has_right else None
+            r.migrate_apply(parts[i][0], from_left, from_right)
 
     def _migration_needed(self) -> bool:
         R = self.ranks
