@@ -201,7 +201,7 @@ struct Mpm {
     int ov_lo[2] = {0, 0}, ov_hi[2] = {0, 0};
     bool g2p_pending = false;          // slab phases: the gather of the last finished substep has not run yet
     float slab_dt = 0.f;               // ... and the dt it has to use
-    int agg = 2;                       // log2 of the longest aggregated run in the scatter (PIXIE_MPM_AGG): 2 measured best at 100k/64^3
+    int agg = 2;                       // log2 of the longest aggregated run in the scatter: PIXIE_MPM_AGG; r02 sweep: 1 and 2 tie at 100k/64^3 and at 1M/256^3, 0 is 10-15 % slower at both
     long long launches = 0;            // kernels of this library launched for this handle (bench.py's gpu_launches)
 };
 
@@ -419,7 +419,7 @@ static void fused_launch(Mpm* m, bool do_g2p, bool do_p2g, bool write_all, float
     const int blocks = (std::max(m->n_active, 1) + B - 1) / B;
     static const bool hoist = !(getenv("PIXIE_MPM_HOIST") && atoi(getenv("PIXIE_MPM_HOIST")) == 0);   // r02 A/B: 23.5 vs 24.1 us
     void (*kern)(const FusedState, const float) = mpm_fused_kernel<2, false>;
-    if (hoist) kern = m->agg == 1 ? mpm_fused_kernel<1, true> : (m->agg == 3 ? mpm_fused_kernel<3, true> : mpm_fused_kernel<2, true>);
+    if (hoist) kern = m->agg == 0 ? mpm_fused_kernel<0, true> : (m->agg == 1 ? mpm_fused_kernel<1, true> : (m->agg == 3 ? mpm_fused_kernel<3, true> : mpm_fused_kernel<2, true>));
     else kern = m->agg == 0 ? mpm_fused_kernel<0, false> : (m->agg == 1 ? mpm_fused_kernel<1, false> : (m->agg == 3 ? mpm_fused_kernel<3, false> : mpm_fused_kernel<2, false>));
     pdl_launch(kern, dim3(blocks), dim3(B), st, t, dt);
     m->launches += 1;
