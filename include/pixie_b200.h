@@ -232,14 +232,17 @@ int pixie_mpm_set_active_count(pixie_mpm_t h, int n_active);
  * [n^3][3] as left by the last substep (for tests). */
 int pixie_mpm_grid_ptrs(pixie_mpm_t h, float** grid_mv4, float** grid_v_out);
 /* ---- Slab mode of the default path (BASELINE config 5, no reference counterpart). Every handle owns an exchange buffer
- * [256-byte flag block][{mv.xyz, m} grid, float4[n_grid^3], x slowest]; pixie_mpm_slab_attach gives it the x-neighbours'
- * buffers (pointers valid in this process: from pixie_ipc_open for a neighbour in another process, or the neighbour's own
- * pointer inside one process). A substep is then three device phases with flag handshakes between neighbours and no host
- * round trip: scatter (particle kernel; stencils may reach `slack` + 2 planes into the neighbours' ranges), halo (overlap
- * totals = own + neighbour partial sums, read over NVLink), finish (grid update on owned + overlap planes, clear).
- * pixie_mpm_step runs whole substeps (CUDA graph); pixie_mpm_slab_phase runs ONE phase (0 scatter, 1 halo, 2 finish) so
+ * [256-byte flag block][{mv.xyz, m} grid 0][grid 1] (float4[n_grid^3] each, x slowest; the two grids alternate by substep
+ * parity); pixie_mpm_slab_attach gives it the x-neighbours' buffers (pointers valid in this process: from pixie_ipc_open for
+ * a neighbour in another process, or the neighbour's own pointer inside one process). A substep is then two launches with
+ * ONE flag handshake between neighbours and no host round trip: scatter (particle kernel; stencils may reach `slack` + 2
+ * planes into the neighbours' ranges) and the grid sweep, which raises this rank's scatter_done, waits for the neighbours'
+ * and adds their partial sums on the shared planes straight from their memory (NVLink) while it updates owned + shared
+ * planes; a rank's own partial sums on shared planes are cleared one substep later (the other grid is in use meanwhile).
+ * pixie_mpm_step runs whole substeps (CUDA graph); pixie_mpm_slab_phase runs ONE phase (0 scatter, 1 nothing, 2 sweep) so
  * that a single-process driver can sequence the phases of several slabs on one stream. Particles whose stencil base
- * leaves [x0 - slack, x1 + slack) raise error 2 (migrate more often); a neighbour that never shows up raises error 1. */
+ * leaves [x0 - slack, x1 + slack) raise error 2 (migrate more often); a neighbour that never shows up raises error 1.
+ * pixie_mpm_set_active_count must be called after every particle migration (it also clears the shared planes). */
 int pixie_mpm_exchange_buffer(pixie_mpm_t h, void** base, size_t* bytes);
 int pixie_mpm_slab_attach(pixie_mpm_t h, int x0, int x1, int slack, const void* left_xbuf, const void* right_xbuf);
 int pixie_mpm_slab_phase(pixie_mpm_t h, int phase, double dt, void* stream);

@@ -171,7 +171,7 @@ struct Mpm {
     float4* grid_v = nullptr;
     DevBC* d_bcs = nullptr;
     bool graph_valid = false;          // false: parameters / BCs changed, captured launches are stale
-    // a few cached CUDA graphs keyed by (substep count, clock parity, dt)
+    // a few cached CUDA graphs keyed by (substep count, clock parity + grid parity, dt)
     static constexpr int kGraphSlots = 4;
     struct GraphSlot { cudaGraphExec_t exec = nullptr; int count = 0, parity = 0, launches = 0; double dt = 0; } graphs[kGraphSlots];
     int graph_next = 0;
@@ -197,7 +197,8 @@ struct Mpm {
     bool slab = false;
     int slab_x0 = 0, slab_x1 = 0, slab_slack = 1;
     const uint8_t* peer_xbuf[2] = {nullptr, nullptr};
-    float4* ov_total[2] = {nullptr, nullptr};
+    float4* grid_mv_alt = nullptr;     // second {mv, m} grid (slab mode alternates between the two by substep parity)
+    int gpar = 0;                      // which of the two grids the next scatter targets (0 outside slab mode)
     int ov_lo[2] = {0, 0}, ov_hi[2] = {0, 0};
     bool g2p_pending = false;          // slab phases: the gather of the last finished substep has not run yet
     float slab_dt = 0.f;               // ... and the dt it has to use
@@ -375,12 +376,16 @@ static void pdl_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, cudaStream
     cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }
 
+static inline size_t grid_bytes(const Mpm* m) { return (size_t)m->n_grid * m->n_grid * m->n_grid * sizeof(float4); }
+static inline float4* scatter_grid(Mpm* m) { return (m->slab && m->gpar) ? m->grid_mv_alt : m->grid_mv; }
+static inline int graph_parity(const Mpm* m) { return m->tpar | (m->gpar << 1); }
+
 static FusedState fused_state(Mpm* m) {
     FusedState t{};
     const Mpm::FsBuf& s = m->fs[0];
     t.f = s.f; t.material = s.material; t.selection = s.selection; t.perm = s.perm;
     t.cap = m->cap; t.n = m->n_active;
-    t.grid_v = m->grid_v; t.grid_mv = m->grid_mv; t.box = m->d_box;
+    t.grid_v = m->grid_v; t.grid_mv = scatter_grid(m); t.box = m->d_box;
     t.bcs = m->d_bcs; t.n_bc = (int)m->bcs.size();
     t.n_particle_bc = 0;
     for (const DevBC& b : m->bcs) {
@@ -425,18 +430,21 @@ static void fused_launch(Mpm* m, bool do_g2p, bool do_p2g, bool write_all, float
     m->launches += 1;
 }
 
-static void gridbox_launch(Mpm* m, float dt, double dt_d, cudaStream_t st) {
+static void gridbox_launch(Mpm* m, bool publish_scatter, float dt, double dt_d, cudaStream_t st) {
     GridBoxArgs g{};
-    g.grid_mv = m->grid_mv; g.grid_v = m->grid_v; g.box = m->d_box;
+    g.grid_mv = scatter_grid(m); g.grid_v = m->grid_v; g.box = m->d_box;
     g.time_in = m->tslots + m->tpar; g.time_out = m->tslots + (m->tpar ^ 1);
     g.pts_in = m->pts + (size_t)m->tpar * kMaxBC * 3; g.pts_out = m->pts + (size_t)(m->tpar ^ 1) * kMaxBC * 3;
     g.bcs = m->d_bcs; g.n_bc = (int)m->bcs.size();
     g.n_grid = m->n_grid; g.x_begin = m->x_begin; g.x_end = m->x_end;
     if (m->slab) {
         g.mine = reinterpret_cast<SlabFlags*>(m->xbuf);
+        g.grid_other = m->gpar ? m->grid_mv : m->grid_mv_alt;
+        g.publish_scatter = publish_scatter ? 1 : 0;
         for (int sd = 0; sd < 2; ++sd) {
             g.peer[sd] = reinterpret_cast<const SlabFlags*>(m->peer_xbuf[sd]);
-            g.total[sd] = m->ov_total[sd]; g.ov_lo[sd] = m->ov_lo[sd]; g.ov_hi[sd] = m->ov_hi[sd];
+            g.peer_mv[sd] = m->peer_xbuf[sd] ? reinterpret_cast<const float4*>(m->peer_xbuf[sd] + sizeof(SlabFlags) + (size_t)m->gpar * grid_bytes(m)) : nullptr;
+            g.ov_lo[sd] = m->ov_lo[sd]; g.ov_hi[sd] = m->ov_hi[sd];
         }
     }
     g.dx = (float)((double)m->grid_lim / (double)m->n_grid);
@@ -446,28 +454,14 @@ static void gridbox_launch(Mpm* m, float dt, double dt_d, cudaStream_t st) {
     pdl_launch(mpm_gridbox_kernel, dim3(296), dim3(256), st, g, dt, dt_d);
     m->launches += 1;
     m->tpar ^= 1;
+    if (m->slab) m->gpar ^= 1;
 }
 
-static void halo_launch(Mpm* m, bool publish_scatter, cudaStream_t st) {
-    HaloArgs a{};
-    a.publish_scatter = publish_scatter ? 1 : 0;
-    a.mine = reinterpret_cast<SlabFlags*>(m->xbuf);
-    a.grid_mv = m->grid_mv; a.box = m->d_box; a.n_grid = m->n_grid;
-    for (int sd = 0; sd < 2; ++sd) {
-        a.peer[sd] = reinterpret_cast<const SlabFlags*>(m->peer_xbuf[sd]);
-        a.peer_mv[sd] = m->peer_xbuf[sd] ? reinterpret_cast<const float4*>(m->peer_xbuf[sd] + sizeof(SlabFlags)) : nullptr;
-        a.total[sd] = m->ov_total[sd]; a.ov_lo[sd] = m->ov_lo[sd]; a.ov_hi[sd] = m->ov_hi[sd];
-    }
-    pdl_launch(mpm_halo_kernel, dim3(148), dim3(256), st, a);          // its last block raises halo_done
-    m->launches += 1;
-}
-
-// `count` substeps as: scatter(0) | [halo(0)] | grid(0) | g2p(0)+scatter(1) | ... | grid(count-1) | g2p(count-1)
+// `count` substeps as: scatter(0) | grid(0) | g2p(0)+scatter(1) | ... | grid(count-1) | g2p(count-1)
 static void fused_batch(Mpm* m, int count, float dt, double dt_d, cudaStream_t st) {
     fused_launch(m, false, true, count == 1, dt, st);
     for (int i = 0; i < count; ++i) {
-        if (m->slab) halo_launch(m, true, st);
-        gridbox_launch(m, dt, dt_d, st);
+        gridbox_launch(m, true, dt, dt_d, st);
         if (i + 1 < count) fused_launch(m, true, true, i + 2 == count, dt, st);
         else fused_launch(m, true, false, true, dt, st);
     }
@@ -477,14 +471,14 @@ static void fused_batch(Mpm* m, int count, float dt, double dt_d, cudaStream_t s
 // slab runs, the chunk between two particle migrations)
 static cudaGraphExec_t fused_graph(Mpm* m, int count, float dt, double dt_d) {
     for (auto& g : m->graphs)
-        if (g.exec && g.count == count && g.parity == m->tpar && g.dt == dt_d) return g.exec;
+        if (g.exec && g.count == count && g.parity == graph_parity(m) && g.dt == dt_d) return g.exec;
     Mpm::GraphSlot& slot = m->graphs[m->graph_next];
     m->graph_next = (m->graph_next + 1) % Mpm::kGraphSlots;
     if (slot.exec) { cudaGraphExecDestroy(slot.exec); slot.exec = nullptr; }
     cudaStream_t cs;
     cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking);
     cudaGraph_t g = nullptr;
-    const int par0 = m->tpar;
+    const int par0 = m->tpar, gpar0 = m->gpar, key0 = graph_parity(m);
     const long long launches0 = m->launches;
     bool ok = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
     if (ok) {
@@ -492,13 +486,13 @@ static cudaGraphExec_t fused_graph(Mpm* m, int count, float dt, double dt_d) {
         ok = cudaStreamEndCapture(cs, &g) == cudaSuccess && g;
     }
     slot.launches = (int)(m->launches - launches0);
-    m->tpar = par0;                                    // capture did not run anything
+    m->tpar = par0; m->gpar = gpar0;                   // capture did not run anything
     m->launches = launches0;
     if (ok) ok = cudaGraphInstantiate(&slot.exec, g, 0) == cudaSuccess;
     if (g) cudaGraphDestroy(g);
     cudaStreamDestroy(cs);
     if (!ok) { cudaGetLastError(); slot.exec = nullptr; return nullptr; }
-    slot.count = count; slot.parity = par0; slot.dt = dt_d;
+    slot.count = count; slot.parity = key0; slot.dt = dt_d;
     return slot.exec;
 }
 
@@ -518,7 +512,7 @@ static int mpm_step_fused(Mpm* m, int n_substeps, double dt_d, cudaStream_t st) 
         if (g) {
             if (cudaGraphLaunch(g, st) != cudaSuccess) { m->error = "cudaGraphLaunch failed"; return 1; }
             for (auto& sl : m->graphs) if (sl.exec == g) m->launches += sl.launches;
-            if (count & 1) m->tpar ^= 1;               // the replay advanced the clock `count` times
+            if (count & 1) { m->tpar ^= 1; if (m->slab) m->gpar ^= 1; }   // the replay advanced the clock `count` times
         } else {
             fused_batch(m, count, dt, dt_d, st);
         }
@@ -571,7 +565,6 @@ void mpm_destroy(Mpm* m) {
     cudaFree(m->d_box); cudaFree(m->tslots); cudaFree(m->pts);
     for (auto& g : m->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
     cudaFree(m->xbuf);
-    cudaFree(m->ov_total[0]); cudaFree(m->ov_total[1]);
     cudaFree(m->grid_v); cudaFree(m->d_bcs);
     delete m;
 }
@@ -595,6 +588,7 @@ int mpm_set_params(Mpm* m, const pixie_mpm_params& p) {
         if (cudaMalloc(&m->xbuf, sizeof(SlabFlags) + nodes * sizeof(float4)) != cudaSuccess ||
             cudaMalloc(&m->grid_v, nodes * sizeof(float4)) != cudaSuccess) { m->error = "cudaMalloc failed"; return 1; }
         m->grid_mv = reinterpret_cast<float4*>(m->xbuf + sizeof(SlabFlags));
+        m->grid_mv_alt = nullptr;
         cudaMemset(m->xbuf, 0, sizeof(SlabFlags) + nodes * sizeof(float4));
         cudaMemset(m->grid_v, 0, nodes * sizeof(float4));
         m->n_grid = p.n_grid;
@@ -706,14 +700,42 @@ int mpm_set_active_count(Mpm* m, int n_active) {
     if (mpm_sync(m, 0)) return 1;          // results of the old live prefix go back first; the next step re-reads the arrays
     m->n_active = n_active;
     m->graph_valid = false;
+    if (m->slab && m->grid_mv_alt) {
+        // Slab mode calls this after every particle migration (all ranks have finished their substeps: the migration's
+        // collectives sit behind them). The shared planes of the grid scattered into last still hold this rank's partial sums
+        // (they are cleared one substep late, inside the node box); particles that just LEFT may have put some outside the
+        // box of the particles that remain, so both grids' shared planes are cleared outright here.
+        const size_t plane = (size_t)m->n_grid * m->n_grid * sizeof(float4);
+        for (int sd = 0; sd < 2; ++sd) {
+            if (!m->peer_xbuf[sd]) continue;
+            const size_t off = (size_t)m->ov_lo[sd] * plane, len = (size_t)(m->ov_hi[sd] - m->ov_lo[sd]) * plane;
+            cudaMemsetAsync(reinterpret_cast<uint8_t*>(m->grid_mv) + off, 0, len, 0);
+            cudaMemsetAsync(reinterpret_cast<uint8_t*>(m->grid_mv_alt) + off, 0, len, 0);
+        }
+    }
     return 0;
 }
 // ---- slab mode (BASELINE config 5, no reference counterpart: the reference hard-wires "cuda:0", gs_simulation.py:441). The exchange buffer [SlabFlags][grid_mv] of each handle is made
 //      visible to its x-neighbours (cudaIpc between processes, plain pointers inside one process); scatter, overlap
 //      exchange and grid update then chain on the device with flag handshakes, no host in the loop.
 int mpm_exchange_buffer(Mpm* m, void** base, size_t* bytes) {
+    // slab mode alternates between two {mv, m} grids (see GridBoxArgs): the first request re-allocates the exchange buffer as
+    // [SlabFlags][grid 0][grid 1], still ONE allocation = one IPC handle
+    const size_t gb = grid_bytes(m);
+    if (!m->grid_mv_alt) {
+        if (mpm_sync(m, 0)) return 1;
+        cudaDeviceSynchronize();
+        uint8_t* nb = nullptr;
+        if (cudaMalloc(&nb, sizeof(SlabFlags) + 2 * gb) != cudaSuccess) { m->error = "cudaMalloc failed (exchange buffer)"; return 1; }
+        cudaMemset(nb, 0, sizeof(SlabFlags) + 2 * gb);
+        cudaFree(m->xbuf);
+        m->xbuf = nb;
+        m->grid_mv = reinterpret_cast<float4*>(nb + sizeof(SlabFlags));
+        m->grid_mv_alt = reinterpret_cast<float4*>(nb + sizeof(SlabFlags) + gb);
+        m->graph_valid = false;
+    }
     *base = m->xbuf;
-    *bytes = sizeof(SlabFlags) + (size_t)m->n_grid * m->n_grid * m->n_grid * sizeof(float4);
+    *bytes = sizeof(SlabFlags) + 2 * gb;
     return 0;
 }
 int mpm_slab_attach(Mpm* m, int x0, int x1, int slack, const void* left_xbuf, const void* right_xbuf) {
@@ -729,14 +751,9 @@ int mpm_slab_attach(Mpm* m, int x0, int x1, int slack, const void* left_xbuf, co
     m->ov_lo[1] = std::max(0, x1 - slack); m->ov_hi[1] = std::min(n, x1 + 2 + slack);
     m->x_begin = left_xbuf ? m->ov_lo[0] : 0;
     m->x_end = right_xbuf ? m->ov_hi[1] : n;
-    for (int sd = 0; sd < 2; ++sd) {
-        cudaFree(m->ov_total[sd]); m->ov_total[sd] = nullptr;
-        if (!m->peer_xbuf[sd]) continue;
-        const size_t bytes = (size_t)(m->ov_hi[sd] - m->ov_lo[sd]) * n * n * sizeof(float4);
-        if (cudaMalloc(&m->ov_total[sd], bytes) != cudaSuccess) { m->error = "cudaMalloc failed (overlap totals)"; return 1; }
-        cudaMemset(m->ov_total[sd], 0, bytes);
-    }
-    cudaMemset(m->xbuf, 0, sizeof(SlabFlags));
+    if (!m->grid_mv_alt) { void* b; size_t nb; if (mpm_exchange_buffer(m, &b, &nb)) return 1; }
+    cudaMemset(m->xbuf, 0, sizeof(SlabFlags) + 2 * grid_bytes(m));
+    m->gpar = 0;
     m->graph_valid = false;
     m->g2p_pending = false;
     return 0;
@@ -754,9 +771,10 @@ int mpm_slab_phase(Mpm* m, int phase, double dt_d, cudaStream_t st) {
         m->launches += 1;
         m->g2p_pending = false;
     } else if (phase == 1) {
-        halo_launch(m, false, st);
+        // nothing to launch: the overlap sums are formed inside the grid sweep (kept so that drivers written for the
+        // scatter / exchange / finish sequence need no special case)
     } else if (phase == 2) {
-        gridbox_launch(m, dt, dt_d, st);
+        gridbox_launch(m, false, dt, dt_d, st);
         m->g2p_pending = true; m->slab_dt = dt;
         ++m->steps_since_sort;
         m->user_stale = true;

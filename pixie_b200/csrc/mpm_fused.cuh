@@ -477,35 +477,12 @@ mpm_fused_kernel(const __grid_constant__ FusedState s, const float dt) {
 // ---- slab exchange block: lives at the start of the handle's exchange buffer, in front of grid_mv, so that ONE
 //      cudaIpc handle (or one pointer in single-process tests) gives a neighbour both the flags and the partial sums
 struct SlabFlags {
-    int scatter_done;     // substep whose scatter into grid_mv is complete and visible
-    int halo_done;        // substep whose overlap totals this rank has finished reading from its neighbours
+    int scatter_done;     // substep whose scatter into this rank's {mv, m} grid (parity k & 1) is complete and visible
     int error;            // 1: a neighbour did not show up in time, 2: a particle drifted beyond the slack planes
     int step;             // this rank's substep counter
-    int halo_blocks;      // blocks of the running halo kernel that are done (the last one raises halo_done)
-    int pad[59];
+    int pad[61];
 };
 static_assert(sizeof(SlabFlags) == 256, "SlabFlags layout");
-
-// Thread 0 of the block polls a neighbour's flag until it reaches `target` (bounded: ~1 s), then the block proceeds.
-__device__ __forceinline__ bool wait_peer_flag(const int* flag, int target, int* my_err) {
-    __shared__ int ok_s;
-    if (threadIdx.x == 0) {
-        int ok = 1;
-        if (flag) {
-            ok = 0;
-            for (long long it = 0; it < (1ll << 22); ++it) {
-                if (ld_acquire_sys(flag) >= target) { ok = 1; break; }
-                __nanosleep(200);
-            }
-            if (!ok) atomicExch(my_err, 1);
-        }
-        ok_s = ok;
-    }
-    __syncthreads();
-    const bool ok = ok_s != 0;
-    __syncthreads();
-    return ok;
-}
 
 // Phase API only (a single-process driver sequences the phases of SEVERAL slabs on one stream and must raise every slab's
 // scatter_done before the first halo launch waits): one thread raises the flag after the particle kernel in front of it.
@@ -518,96 +495,20 @@ __global__ void mpm_publish_kernel(SlabFlags* mine) {
     }
 }
 
-struct HaloArgs {
-    SlabFlags* mine;
-    const SlabFlags* peer[2];       // left, right neighbour (nullptr at the domain ends)
-    const float4* peer_mv[2];
-    const float4* grid_mv;
-    float4* total[2];               // [ov planes][n][n]: own + neighbour partial sums on the planes shared with that neighbour
-    const int* box;
-    int n_grid;
-    int ov_lo[2], ov_hi[2];         // shared plane ranges [lo, hi)
-    int publish_scatter;            // 1: this launch also raises scatter_done (chained runs); 0: a publish launch did (phase API)
-};
-
-// Overlap totals: total = own partial + neighbour's partial on the shared planes, inside this rank's node box (the only
-// nodes its particles read). Neither partial is modified here, so both neighbours compute the same sums (a + b == b + a).
-__global__ void __launch_bounds__(256)
-mpm_halo_kernel(const HaloArgs a) {
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    asm volatile("griddepcontrol.wait;" ::: "memory");          // this rank's scatter of the substep is complete
-    const int k = a.mine->step;
-    const int n = a.n_grid;
-    const int ly = a.box[1], lz = a.box[2], hy = a.box[4], hz = a.box[5];
-    const int ey = hy - ly, ez = hz - lz;
-    // the particle kernel in front of this launch has completed (griddepcontrol.wait / stream order): tell the neighbours that
-    // this rank's partial sums of substep k are in place BEFORE waiting for theirs (release at system scope: they read them
-    // over NVLink). The particle kernel itself stays free of fences: its reds remain fire-and-forget.
-    if (a.publish_scatter && blockIdx.x == 0 && threadIdx.x == 0) {
-        __threadfence_system();
-        st_release_sys(&a.mine->scatter_done, k);
-    }
-    // both neighbours' flags are awaited at the same time (two polling threads), then ONE pass covers both overlaps: the
-    // remote reads of the two sides are in flight together
-    __shared__ int ok_s[2];
-    if (threadIdx.x < 64 && (threadIdx.x & 31) == 0) {
-        const int side = threadIdx.x >> 5;
-        int ok = 1;
-        if (a.peer[side]) {
-            ok = 0;
-            for (long long it = 0; it < (1ll << 22); ++it) {
-                if (ld_acquire_sys(&a.peer[side]->scatter_done) >= k) { ok = 1; break; }
-                __nanosleep(100);
-            }
-            if (!ok) atomicExch(&a.mine->error, 1);
-        }
-        ok_s[side] = ok;
-    }
-    __syncthreads();
-    const bool ok = ok_s[0] && ok_s[1];
-    long long cnt[2], off[2] = {0, 0};
-    int lxs[2], exs[2];
-#pragma unroll
-    for (int side = 0; side < 2; ++side) {
-        lxs[side] = max(a.ov_lo[side], a.box[0]);
-        exs[side] = min(a.ov_hi[side], a.box[3]) - lxs[side];
-        cnt[side] = (a.peer[side] && exs[side] > 0 && ey > 0 && ez > 0) ? (long long)exs[side] * ey * ez : 0;
-    }
-    off[1] = cnt[0];
-    const long long total = cnt[0] + cnt[1];
-    if (ok)
-        for (long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; t0 < total; t0 += (long long)gridDim.x * blockDim.x) {
-            const int side = t0 >= off[1] ? 1 : 0;
-            const long long t = t0 - off[side];
-            const int iz = (int)(t % ez), iy = (int)((t / ez) % ey), ix = (int)(t / ((long long)ez * ey));
-            const size_t idx = ((size_t)(lxs[side] + ix) * n + (ly + iy)) * n + (lz + iz);
-            const float4 own = a.grid_mv[idx];
-            const float4 oth = a.peer_mv[side][idx];                 // peer memory (NVLink) or the other slab of a test
-            const size_t tix = ((size_t)(lxs[side] + ix - a.ov_lo[side]) * n + (ly + iy)) * n + (lz + iz);
-            a.total[side][tix] = make_float4(own.x + oth.x, own.y + oth.y, own.z + oth.z, own.w + oth.w);
-        }
-    // the last block raises halo_done: the neighbours may now clear what this rank has read
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        const int done = atomicAdd(&a.mine->halo_blocks, 1);
-        if (done == (int)gridDim.x - 1) {
-            a.mine->halo_blocks = 0;
-            __threadfence_system();
-            if (ok) st_release_sys(&a.mine->halo_done, k);
-        }
-    }
-}
-
 struct GridBoxArgs {
-    float4* grid_mv;
+    float4* grid_mv;             // the {mv, m} grid the particle kernel of this substep scattered into
     float4* grid_v;
-    // slab mode (else mine == nullptr): planes [ov_lo, ov_hi) of side s take their {mv, m} from total[s]; the sweep waits
-    // until the neighbours have read this rank's partial sums of the substep before it clears them
+    // slab mode (else mine == nullptr). Each rank keeps TWO {mv, m} grids and alternates between them by substep parity:
+    // on the planes [ov_lo, ov_hi) shared with neighbour s the sweep adds the neighbour's partial sums of the same parity,
+    // read straight from its memory (NVLink) after ONE flag handshake, and leaves its own partial sums there untouched (the
+    // neighbour reads them at the same time); they are cleared one substep later (grid_other), when the neighbour's
+    // scatter_done of that substep proves its sweep of this one has finished.
     SlabFlags* mine;
     const SlabFlags* peer[2];
-    const float4* total[2];
+    const float4* peer_mv[2];    // the neighbours' grids of this substep's parity
+    float4* grid_other;          // this rank's grid of the other parity
     int ov_lo[2], ov_hi[2];
+    int publish_scatter;         // 1: raise scatter_done here (chained runs); 0: a publish launch did (phase API)
     const int* box;              // lo.xyz, hi.xyz
     const double* time_in; double* time_out;
     const float* pts_in; float* pts_out;       // [n_bc][3] collider points, by parity (the cuboid ones move)
@@ -621,9 +522,31 @@ mpm_gridbox_kernel(const GridBoxArgs s, const float dt, const double dt_d) {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
     if (s.mine) {
+        // the particle kernel in front of this launch has completed (griddepcontrol.wait / stream order): tell the neighbours
+        // that this rank's partial sums of substep k are in place BEFORE waiting for theirs (release at system scope: they
+        // read them over NVLink). The particle kernel stays free of fences: its reds remain fire-and-forget.
         const int k = s.mine->step;
-        for (int side = 0; side < 2; ++side)
-            if (s.peer[side] && !wait_peer_flag(&s.peer[side]->halo_done, k, &s.mine->error)) return;
+        if (s.publish_scatter && blockIdx.x == 0 && threadIdx.x == 0) {
+            __threadfence_system();
+            st_release_sys(&s.mine->scatter_done, k);
+        }
+        // both neighbours are awaited at the same time (two polling threads per block, bounded)
+        __shared__ int ok_s[2];
+        if (threadIdx.x < 64 && (threadIdx.x & 31) == 0) {
+            const int side = threadIdx.x >> 5;
+            int ok = 1;
+            if (s.peer[side]) {
+                ok = 0;
+                for (long long it = 0; it < (1ll << 22); ++it) {
+                    if (ld_acquire_sys(&s.peer[side]->scatter_done) >= k) { ok = 1; break; }
+                    __nanosleep(100);
+                }
+                if (!ok) atomicExch(&s.mine->error, 1);
+            }
+            ok_s[side] = ok;
+        }
+        __syncthreads();
+        if (!(ok_s[0] && ok_s[1])) return;
     }
     const int n = s.n_grid;
     const int lx = max(s.box[0], s.x_begin), ly = s.box[1], lz = s.box[2];
@@ -654,11 +577,15 @@ mpm_gridbox_kernel(const GridBoxArgs s, const float dt, const double dt_d) {
         const size_t idx = ((size_t)gx * n + gy) * n + gz;
         const float4 own = s.grid_mv[idx];
         float4 mv = own;
+        bool shared_plane = false;
         if (s.mine) {
 #pragma unroll
             for (int side = 0; side < 2; ++side)
-                if (s.peer[side] && gx >= s.ov_lo[side] && gx < s.ov_hi[side])
-                    mv = s.total[side][((size_t)(gx - s.ov_lo[side]) * n + gy) * n + gz];
+                if (s.peer[side] && gx >= s.ov_lo[side] && gx < s.ov_hi[side]) {
+                    const float4 oth = s.peer_mv[side][idx];       // neighbour's memory; own + oth == oth + own on its side
+                    mv = make_float4(own.x + oth.x, own.y + oth.y, own.z + oth.z, own.w + oth.w);
+                    shared_plane = true;
+                }
         }
         float vx = 0.f, vy = 0.f, vz = 0.f;
         if (mv.w > 1e-15f) {                                   // grid_normalization_and_gravity :398-409
@@ -709,7 +636,8 @@ mpm_gridbox_kernel(const GridBoxArgs s, const float dt, const double dt_d) {
             }
         }
         s.grid_v[idx] = make_float4(vx, vy, vz, 0.f);
-        if (own.x != 0.f || own.y != 0.f || own.z != 0.f || own.w != 0.f) s.grid_mv[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (shared_plane) s.grid_other[idx] = make_float4(0.f, 0.f, 0.f, 0.f);      // last substep's sums: the neighbour is done with them
+        else if (own.x != 0.f || own.y != 0.f || own.z != 0.f || own.w != 0.f) s.grid_mv[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
 }
 

@@ -16,9 +16,12 @@ update there is computed redundantly and no second exchange is needed.
 
 Two exchange mechanisms behind one orchestration:
   * `FusedSlabBackend` (the product): the exchange runs ON THE DEVICE. Every handle exposes an exchange buffer
-    [flags][grid]; neighbours map each other's buffers (cudaIpc over NVLink between processes) and the halo kernel reads
-    the neighbour's partial sums directly, after a flag handshake; scatter -> halo -> finish chain in one CUDA graph, the
-    host only steps in for particle migration (NCCL send/recv of packed records).
+    [flags][grid 0][grid 1]; neighbours map each other's buffers (cudaIpc over NVLink between processes). The grid sweep
+    raises this rank's `scatter_done`, waits for the neighbours' (bounded) and adds their partial sums on the shared planes
+    straight from their memory; the two grids alternate by substep parity so that a rank's own partial sums can stay in
+    place while the neighbour reads them (no second handshake, no staging copy). scatter -> sweep chain in one CUDA graph
+    per chunk of substeps; the host only steps in at migration check points (an 8-byte all-reduce; NCCL send/recv of packed
+    records when particles really have to move).
   * host exchange (`planes` / `planes_add`): what the CPU test double (tests/slab_backends.py) implements, so that the
     orchestration — overlap ranges, migration, id bookkeeping — is exercised without a GPU, in one process and over gloo.
 
@@ -106,7 +109,7 @@ class FusedSlabBackend:
         self._phase(0, dt)
 
     def halo(self, dt: float):
-        self._phase(1, dt)
+        self._phase(1, dt)          # no launch on this backend: the overlap sums are formed inside the grid sweep (finish)
 
     def finish(self, dt: float, lo: int, hi: int):
         self._phase(2, dt)
@@ -135,10 +138,12 @@ class FusedSlabBackend:
     def active(self) -> int:
         return self._active
 
-    def set_active(self, n: int):
+    def set_active(self, n: int, force: bool = False):
+        """Live prefix length. `force` (after a migration, even when the count is unchanged: the SET changed) lets the
+        library reset what depends on the particle set (graphs, leftovers on the shared planes)."""
         if n > self.capacity:
             raise RuntimeError(f"slab holds {n} particles but was created with capacity {self.capacity}")
-        if n != self._active:
+        if n != self._active or force:
             self._check(self.lib.pixie_mpm_set_active_count(self.solver._handle, int(n)))
             self._active = int(n)
 
@@ -171,7 +176,7 @@ class FusedSlabBackend:
                 src = arrivals[:, c:c + w].contiguous()
                 full[n_keep:n_keep + n_new] = src.view(torch.int32) if full.dtype == torch.int32 else src
             c += w
-        self.set_active(n_keep + n_new)
+        self.set_active(n_keep + n_new, force=(n_keep != old or n_new > 0))
 
 
 # ------------------------------------------------------------------------------------------- orchestration
