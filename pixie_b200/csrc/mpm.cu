@@ -30,7 +30,7 @@ using namespace mpm;
 
 namespace {
 
-constexpr int kMaxBC = 96;     // release_particles_sequentially registers 50 modifiers on its own
+constexpr int kMaxBC = 256;    // release_particles_sequentially registers 50 modifiers per call (two calls + a scene's own BCs fit)
 
 struct DevBC {
     int kind;

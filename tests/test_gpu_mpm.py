@@ -94,6 +94,23 @@ def test_rotation_modifier_and_cylinder_selection(built_lib, cuda_dev):
     assert gm.sum() > 20 and _err(s, o, "X") < 1e-5
 
 
+def test_two_sequential_releases_fit_the_bc_table(built_lib, cuda_dev):
+    """release_particles_sequentially registers 50 velocity modifiers per call (mpm_solver_warp.py:1183-1210): two calls plus the
+    scene's own conditions must fit the device table; a table overflow must raise instead of dropping conditions."""
+    from pixie_b200 import _lib
+    s, o, sc = _pair(2000, 32, (0,), seed=3, bcs=False)
+    for _ in range(2):
+        s.release_particles_sequentially(normal=[0, 0, 1], start_position=0.7, end_position=1.3, num_layers=50, start_time=0.0, end_time=0.01)
+    s.add_bounding_box()
+    s.p2g2p_n(8, 1e-4)
+    torch.cuda.synchronize()
+    x = s.export_particle_x_to_torch().cpu().numpy()
+    assert np.isfinite(x).all()
+    with pytest.raises(_lib.PixieError, match="too many boundary conditions"):
+        for _ in range(4):
+            s.release_particles_sequentially(normal=[0, 0, 1], start_position=0.7, end_position=1.3, num_layers=50, start_time=0.0, end_time=0.01)
+
+
 def test_setup_and_export_kernels(built_lib, cuda_dev):
     s, o, sc = _pair(3000, 32, (0,), seed=5, bcs=False)
     n = 3000
