@@ -482,7 +482,7 @@ def run_ours(args, emit):
                 "peak_source": pk["src"] + ", sustained bf16",
                 # dram__bytes_read.sum + dram__bytes_write.sum of ONE dominant launch (64->64 3x3x3 @ 64^3, 58.0 GFLOP, algorithmic
                 # bytes 100.9 MB) from the committed ncu --set full capture (profiles/r01_final_summary.md section 3)
-                "traffic": 48.6e6, "traffic_launch": "64->64 3x3x3 conv @ 64^3 (fp16 pass): algorithmic 100.9e6 B, ncu dram 48.6e6 B",
+                "traffic": 234.9e6, "traffic_launch": "128->128 3x3x3 conv @ 64^3, fp16e5 (the longest launch of a network): algorithmic 268.4e6 B (fp16 + E5M2 operands in, fp32 out), ncu dram__bytes 136.3e6 read + 98.7e6 written (profiles/r02_ncu_full_summary.md)",
                 "note": "achieved = algorithmic FLOPs (2*MACs of the reference graph) / sum of conv launch times from CUDA events; "
                         + {"fp16x3": "fp16x3 executes 3 fp16 tensor-core passes per algorithmic FLOP (ceiling 1/3)",
                            "fp16e5": "fp16e5 executes one fp16 pass + one E5M2 pass at twice the rate = 2 pass-equivalents per algorithmic FLOP (ceiling 1/2)",
@@ -492,7 +492,8 @@ def run_ours(args, emit):
         sub_s = ms_mpm * 1e-3 / (args.steps * SUB)
         roof_mpm = {"kernel": "mpm substep: mpm_fused_kernel (g2p + stress + p2g) + mpm_gridbox_kernel", "bound": "hbm", "achieved": per_sub_bytes / sub_s * 1e-9,
                     "peak": pk["hbm"], "unit": "GB/s", "frac": per_sub_bytes / sub_s * 1e-9 / pk["hbm"], "peak_source": pk["src"],
-                    "traffic": None, "algorithmic_bytes_per_substep": per_sub_bytes, "us_per_substep": sub_s * 1e6}
+                    "traffic": 8.7e6, "traffic_note": "ncu dram__bytes of mpm_fused_kernel per launch at 100k / 64^3 (8.5e6 read + 0.2e6 written): the working set is L2-resident",
+                    "algorithmic_bytes_per_substep": per_sub_bytes, "us_per_substep": sub_s * 1e6}
         # counted, not estimated: the U-Net executors and the MPM handle count the kernels they enqueue (graph replays count their nodes)
         n_launch = int(round(args.steps * (pred.seg_network.launch_count() + pred.cont_network.launch_count() + mpm_launches_per_rollout)))
 

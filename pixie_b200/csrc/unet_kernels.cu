@@ -206,62 +206,86 @@ upsample2_kernel(const float* __restrict__ x, __half* __restrict__ y, __half* __
 
 // ------------------------------------------------------------------------------------ attention
 // qkv: fp32 [NB][T][3C] (q | k | v along channels, Conv1d output order, diffusion_network.py:233)
-// out: fp16 [NB][T][C] = softmax_s((q_t . k_s) / sqrt(C)) v_s.   One block per (query token, nb).
+// out: fp16 [NB][T][C] = softmax_s((q_t . k_s) / sqrt(C)) v_s.   One block per kAttnQ query tokens: every key / value row is
+// loaded once per block and used for all of them (one query per block re-read K and V 512 times from L2: 230 us per launch,
+// r02 launch list); a warp reads a key row as one coalesced line per 128 channels and reduces the kAttnQ dot products by shuffles.
+constexpr int kAttnQ = 4;
 __global__ void __launch_bounds__(256)
 attention_kernel(const float* __restrict__ qkv, __half* __restrict__ out, __half* __restrict__ out_lo, int lo_mode, int T, int C) {
-    extern __shared__ float sm[];
-    float* qs = sm;            // C
-    float* sc = sm + C;        // T
-    __shared__ float red[32];
-    const int t = blockIdx.x, nb = blockIdx.y;
+    extern __shared__ __align__(16) float sm[];
+    float* qs = sm;                    // [kAttnQ][C]
+    float* sc = sm + kAttnQ * C;       // [kAttnQ][T]
+    __shared__ float inv_s[kAttnQ];
+    const int t0 = blockIdx.x * kAttnQ, nb = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
     const float* base = qkv + (size_t)nb * T * 3 * C;
     const float scale = rsqrtf(sqrtf((float)C));     // applied to q and to k (diffusion_network.py:235-238)
-    for (int c = threadIdx.x; c < C; c += blockDim.x) qs[c] = base[(size_t)t * 3 * C + c] * scale;
+    for (int i = threadIdx.x; i < kAttnQ * C; i += blockDim.x) {
+        const int q = i / C, c = i - q * C;
+        qs[i] = (t0 + q < T) ? base[(size_t)(t0 + q) * 3 * C + c] * scale : 0.f;
+    }
     __syncthreads();
-    float lmax = -INFINITY;
-    for (int s = threadIdx.x; s < T; s += blockDim.x) {
+    // ---- scores: warp w takes keys w, w + nwarp, ...
+    for (int s = warp; s < T; s += nwarp) {
         const float4* kp = reinterpret_cast<const float4*>(base + (size_t)s * 3 * C + C);
-        float acc = 0.f;
-        for (int c4 = 0; c4 < C / 4; ++c4) {
-            const float4 kv = __ldg(kp + c4);
-            acc += qs[4 * c4] * (kv.x * scale) + qs[4 * c4 + 1] * (kv.y * scale) +
-                   qs[4 * c4 + 2] * (kv.z * scale) + qs[4 * c4 + 3] * (kv.w * scale);
+        float part[kAttnQ];
+#pragma unroll
+        for (int q = 0; q < kAttnQ; ++q) part[q] = 0.f;
+        for (int c4 = lane; c4 < C / 4; c4 += 32) {
+            float4 kv = __ldg(kp + c4);
+            kv.x *= scale; kv.y *= scale; kv.z *= scale; kv.w *= scale;
+#pragma unroll
+            for (int q = 0; q < kAttnQ; ++q) {
+                const float4 qv = *reinterpret_cast<const float4*>(qs + q * C + 4 * c4);
+                part[q] += qv.x * kv.x + qv.y * kv.y + qv.z * kv.z + qv.w * kv.w;
+            }
         }
-        sc[s] = acc;
-        lmax = fmaxf(lmax, acc);
+#pragma unroll
+        for (int q = 0; q < kAttnQ; ++q) {
+            float v = part[q];
+            for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) sc[q * T + s] = v;
+        }
     }
-    // block max
-    for (int o = 16; o; o >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffff, lmax, o));
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = lmax;
     __syncthreads();
-    float bmax = red[0];
-    for (int i = 1; i < (int)(blockDim.x >> 5); ++i) bmax = fmaxf(bmax, red[i]);
-    __syncthreads();
-    float lsum = 0.f;
-    for (int s = threadIdx.x; s < T; s += blockDim.x) {
-        const float e = __expf(sc[s] - bmax);
-        sc[s] = e;
-        lsum += e;
+    // ---- softmax: warp q normalises query q
+    if (warp < kAttnQ) {
+        float* row = sc + warp * T;
+        float mx = -INFINITY;
+        for (int s = lane; s < T; s += 32) mx = fmaxf(mx, row[s]);
+        for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        float sum = 0.f;
+        for (int s = lane; s < T; s += 32) { const float e = __expf(row[s] - mx); row[s] = e; sum += e; }
+        for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        if (lane == 0) inv_s[warp] = 1.f / sum;
     }
-    for (int o = 16; o; o >>= 1) lsum += __shfl_xor_sync(0xffffffff, lsum, o);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = lsum;
     __syncthreads();
-    float bsum = 0.f;
-    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) bsum += red[i];
-    const float inv = 1.f / bsum;
+    // ---- weighted values: one channel per thread, every value row read once for the kAttnQ queries
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        float acc = 0.f;
-        for (int s = 0; s < T; ++s) acc += sc[s] * __ldg(base + (size_t)s * 3 * C + 2 * C + c);
-        const float val = acc * inv;
-        const __half hv = __float2half_rn(val);
-        out[((size_t)nb * T + t) * C + c] = hv;
-        const size_t idx = ((size_t)nb * T + t) * C + c;
-        if (out_lo && lo_mode == 1) {
-            constexpr float up = (float)(1 << kF8Shift), down = 1.0f / (float)(1 << kF8Shift);
-            uint8_t* row = reinterpret_cast<uint8_t*>(out_lo) + 2 * (idx & ~(size_t)63) + (idx & 63);
-            row[0] = (uint8_t)__nv_cvt_float_to_fp8((val - __half2float(hv)) * up, __NV_SATFINITE, __NV_E5M2);
-            row[64] = (uint8_t)__nv_cvt_float_to_fp8(val * down, __NV_SATFINITE, __NV_E5M2);
-        } else if (out_lo) out_lo[idx] = __float2half_rn(val - __half2float(hv));
+        float acc[kAttnQ];
+#pragma unroll
+        for (int q = 0; q < kAttnQ; ++q) acc[q] = 0.f;
+        const float* vp = base + 2 * C + c;
+#pragma unroll 4
+        for (int s = 0; s < T; ++s) {
+            const float v = __ldg(vp + (size_t)s * 3 * C);
+#pragma unroll
+            for (int q = 0; q < kAttnQ; ++q) acc[q] = fmaf(sc[q * T + s], v, acc[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < kAttnQ; ++q) {
+            if (t0 + q >= T) break;
+            const float val = acc[q] * inv_s[q];
+            const __half hv = __float2half_rn(val);
+            const size_t idx = ((size_t)nb * T + t0 + q) * C + c;
+            out[idx] = hv;
+            if (out_lo && lo_mode == 1) {
+                constexpr float up = (float)(1 << kF8Shift), down = 1.0f / (float)(1 << kF8Shift);
+                uint8_t* row = reinterpret_cast<uint8_t*>(out_lo) + 2 * (idx & ~(size_t)63) + (idx & 63);
+                row[0] = (uint8_t)__nv_cvt_float_to_fp8((val - __half2float(hv)) * up, __NV_SATFINITE, __NV_E5M2);
+                row[64] = (uint8_t)__nv_cvt_float_to_fp8(val * down, __NV_SATFINITE, __NV_E5M2);
+            } else if (out_lo) out_lo[idx] = __float2half_rn(val - __half2float(hv));
+        }
     }
 }
 
@@ -349,9 +373,9 @@ int launch_upsample2(const float* x, __half* y, __half* ylo, int lo_mode, int NB
 }
 
 int launch_attention(const float* qkv, __half* out, __half* out_lo, int lo_mode, int NB, int T, int C, cudaStream_t st) {
-    const size_t smem = (size_t)(C + T) * sizeof(float);
-    if (smem > 48 * 1024) return 1;
-    dim3 grid(T, NB);
+    const size_t smem = (size_t)kAttnQ * (C + T) * sizeof(float);
+    if (smem > 48 * 1024 || C % 4) return 1;
+    dim3 grid((T + kAttnQ - 1) / kAttnQ, NB);
     attention_kernel<<<grid, 256, smem, st>>>(qkv, out, out_lo, lo_mode, T, C);
     return (int)cudaGetLastError();
 }
