@@ -554,6 +554,9 @@ def run_ours(args, emit):
         "dtype": args.precision + " (U-Net, fp32 accumulate) + f32 (MPM)", "data": "synthetic",
         "config": workload_config(args), "precision": args.precision,
         "unet_ms_per_scene": ms_unet / K, "mpm_ms_per_rollout": ms_mpm / K,
+        "unet_streams": 1 if os.environ.get("PIXIE_UNET_STREAMS", "2") == "1" else 2,
+        "unet_streams_note": "the two networks of a scene run concurrently on two streams (CUDA-graph replays); unet_kernel_breakdown_ms and roofline use "
+                             "per-launch CUDA events of each network run ALONE, so their sum may exceed unet_ms_per_scene",
         "mpm": {"metric": "mpm_particle_steps_per_s", "value": pps, "unit": "particle-steps/s", "us_per_substep": ms_mpm / K / SUB * 1e3,
                 "variants": variants},
         "mpm_slab": slab,

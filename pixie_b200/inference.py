@@ -6,6 +6,7 @@ process_batch's forward + argmax (:122-126) and save_predictions' (3 + n_classes
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -30,6 +31,8 @@ class MaterialFieldPredictor:
         self.grid_size, self.feature_channels = grid_size, feature_channels
         self.n_classes, self.max_batch = num_material_classes, max_batch
         self._pipe = None
+        self._side: Optional[torch.cuda.Stream] = None
+        self._two_streams = os.environ.get("PIXIE_UNET_STREAMS", "2") != "1"
         self._feat_dev: Optional[torch.Tensor] = None
         self._packed_dev: Optional[torch.Tensor] = None
 
@@ -39,9 +42,27 @@ class MaterialFieldPredictor:
         return self
 
     def predict(self, feat_ndhwc_f16: torch.Tensor, seg_out: Optional[torch.Tensor] = None, cont_out: Optional[torch.Tensor] = None):
-        """Device fp16 (N, D, H, W, C) -> (seg_logits (N, n_classes, D,H,W), cont_pred (N, 3, D,H,W)) fp32."""
-        return (self.seg_network.forward_channels_last_f16(feat_ndhwc_f16, seg_out),
-                self.cont_network.forward_channels_last_f16(feat_ndhwc_f16, cont_out))
+        """Device fp16 (N, D, H, W, C) -> (seg_logits (N, n_classes, D,H,W), cont_pred (N, 3, D,H,W)) fp32.
+
+        The two networks are independent (inference_combined.py:122-126 calls them one after the other on the same grid): the
+        regression network is enqueued on a side stream, so that the latency-bound 8^3 / 16^3 levels of one network (a few
+        dozen 20-us launches that fill a fraction of the SMs) overlap with the other network's work. Both forwards are CUDA-graph
+        replays; the caller's stream waits for the side stream before this returns."""
+        if not self._two_streams:
+            return (self.seg_network.forward_channels_last_f16(feat_ndhwc_f16, seg_out),
+                    self.cont_network.forward_channels_last_f16(feat_ndhwc_f16, cont_out))
+        main = torch.cuda.current_stream(self.device)
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        side = self._side
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            cont = self.cont_network.forward_channels_last_f16(feat_ndhwc_f16, cont_out)
+        seg = self.seg_network.forward_channels_last_f16(feat_ndhwc_f16, seg_out)
+        main.wait_stream(side)
+        cont.record_stream(main)
+        feat_ndhwc_f16.record_stream(side)
+        return seg, cont
 
     def pack(self, seg_logits: torch.Tensor, cont_pred: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """(N, 3 + n_classes, D, H, W): continuous channels + one-hot argmax, as sample_*_pred.npy."""
