@@ -87,10 +87,9 @@ struct ConvKernelParams {
 
 // One activation source of a convolution.
 struct ConvSrc {
-    const __half* ptr;    // NDHWC fp16, [NB][Din][Hin][Win][C]; with wpad: [NB][Din][Hin][Win + 2][C], columns 0 and Win + 1 zero
+    const __half* ptr;    // NDHWC fp16, [NB][Din][Hin][Win][C]
     int C;                // channels (multiple of 64)
     int Din, Hin, Win;
-    int wpad = 0;         // 1: W-padded storage (inputs of the flat-plane kernel, conv_flat.cu)
 };
 
 // Host description of one convolution launch.
@@ -142,58 +141,6 @@ struct ConvPlan {
     bool fused_stats = false;  // the epilogue accumulates ConvDesc::stats (needs split_k == 1, Cout <= 256)
     size_t out_bytes = 0;
 };
-
-// ---- flat-plane kernel (conv_flat.cu): 3x3x3 stride-1 convolutions at W = 64 / 32 whose sources are stored W-padded.
-// A tile is 128 CONSECUTIVE rows of the flattened padded plane ([H][W+2] voxels), so tap (kh, kw) is the same shared-memory
-// slab read from row kh*(W+2) + kw (tcgen05 SW128 operands may start at any 128-byte row: rowoff_test.cu), one slab per
-// input plane serves all 9 (kh, kw) taps x 3 kd, and the 27 tap tiles of a 64-channel K segment stay resident (each CTA
-// owns 32 output channels = 108 KB of weights).
-struct FlatItem {         // one K segment: (source, 64-channel chunk, operand kind), 27 taps or the centre tap only
-    int8_t src;           // tensor-map index
-    int8_t f8;            // E5M2 correction segment
-    int8_t ntaps;         // 27 or 1
-    int8_t pad_;
-    int16_t c0;           // first channel (2-byte units) of the chunk inside the source
-    int16_t pad2_;
-    int32_t wtile_base;   // first weight tile (64 K-columns each): 27-tap segments hold (kh, kw) major, kd = 2, 1, 0 inside
-};
-constexpr int kFlatMaxItems = 16;
-constexpr int kFlatTD = 4;            // output planes per tile
-constexpr int kFlatG = 2;             // tiles per work unit (accumulators of one set: G x TD x 32 columns = 256)
-constexpr int kFlatNH = 32;           // output channels per CTA
-constexpr int kFlatSlabRows = 272;    // 2 TMA boxes of 136 rows >= 128 + 2 (W + 2) + 2
-constexpr int kFlatSStages = 3;
-
-struct FlatKernelParams {
-    CUtensorMap tmA[kConvMaxSrc];     // [C][H * (W + 2)][D][NB], box [64][136][1][1]
-    CUtensorMap tmB;                  // packed weights [K][Cout_pad], box [64][32]
-    FlatItem items[kFlatMaxItems];
-    int n_items;
-    int NB, D, H, W, Wp;
-    int tiles_per_plane, groups_per_plane, tiles_d, n_halves, total_units;
-    int Cout;
-    const float* bias;
-    const float* residual;
-    float* out;
-    int out_ld;
-    double* stats;
-    int stats_ld, stats_scalar;
-    int* err_flag;
-    int debug_flags;
-};
-struct FlatPlan {
-    FlatKernelParams p{};
-    int grid = 0, smem_bytes = 0;
-    bool fused_stats = false;
-};
-// true when `d` can run on the flat-plane kernel (3x3x3 / fused 1x1 segments, stride 1, W in {32, 64}, Cout % 32 == 0, every
-// source W-padded, NDHWC output)
-bool conv_flat_eligible(const ConvDesc& d);
-void conv_flat_pack_weights(const ConvDesc& d, const std::vector<const float*>& seg_weights, const std::vector<int>& seg_cin_real,
-                            std::vector<__half>& packed);
-int conv_flat_plan_create(const ConvDesc& d, int* d_err_flag, FlatPlan& plan, char* err, int errlen);
-int conv_flat_plan_launch(const FlatPlan& plan, cudaStream_t stream);
-int conv_flat_plan_retarget(const ConvDesc& d, FlatPlan& plan, char* err, int errlen);
 
 // Returns 0 on success; on failure returns non-zero and fills `err`.
 int conv_plan_create(const ConvDesc& d, int* d_err_flag, ConvPlan& plan, char* err, int errlen);
