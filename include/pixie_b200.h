@@ -228,8 +228,9 @@ int pixie_mpm_select_cylinder(pixie_mpm_t h, const float point[3], const float n
 int pixie_mpm_sync(pixie_mpm_t h, void* stream);
 /* Live particles = the prefix [0, n_active) of the bound arrays (slab runs migrate particles between ranks). */
 int pixie_mpm_set_active_count(pixie_mpm_t h, int n_active);
-/* Borrowed pointers to the grid arrays owned by the handle: grid_m [n^3], grid_v_in / grid_v_out
- * [n^3][3] as left by the last substep (for tests). */
+/* Borrowed pointers to the grid arrays owned by the handle (for tests): the {mv.xyz, m} float4[n^3] scatter grid (cleared by
+ * the sweep that consumed it; in slab mode this is grid 0 of the two) and the {v.xyz, 0} float4[n^3] velocities the last
+ * substep's sweep wrote. */
 int pixie_mpm_grid_ptrs(pixie_mpm_t h, float** grid_mv4, float** grid_v_out);
 /* ---- Slab mode of the default path (BASELINE config 5, no reference counterpart). Every handle owns an exchange buffer
  * [256-byte flag block][{mv.xyz, m} grid 0][grid 1] (float4[n_grid^3] each, x slowest; the two grids alternate by substep
