@@ -65,8 +65,14 @@ __device__ __forceinline__ void svd3(const M3& F, M3& U, V3& sig, M3& V) {
     for (int c = 0; c < 3; ++c)
 #pragma unroll
         for (int r = 0; r < 3; ++r) { b[c][r] = F.m[3 * r + c]; v[c][r] = (r == c) ? 1.f : 0.f; }
+    // Rotation of a column pair: with d = be - al, g = 2 ga, h = sqrt(d^2 + g^2) the textbook
+    //   zeta = d / g, t = sign(zeta) / (|zeta| + sqrt(1 + zeta^2)), c = 1 / sqrt(1 + t^2), s = c t
+    // is c^2 = (1 + |d| / h) / 2, s = sign(d) g / (2 h c): two rsqrt (one Newton step each: c^2 + s^2 = 1 to 3e-7) instead of
+    // three IEEE divisions and two square roots (~60 instructions per rotation, r02 ncu). A sweep that rotates nothing ends
+    // the iteration (a pair counts as orthogonal below |cos| = 3e-7 ~ 5 ulp; the fixed five sweeps kept rotating rounding noise).
 #pragma unroll 1
     for (int sweep = 0; sweep < 5; ++sweep) {
+        bool rotated = false;
 #pragma unroll
         for (int pair = 0; pair < 3; ++pair) {
             const int p = (pair == 2) ? 1 : 0;
@@ -74,11 +80,17 @@ __device__ __forceinline__ void svd3(const M3& F, M3& U, V3& sig, M3& V) {
             const float al = b[p][0] * b[p][0] + b[p][1] * b[p][1] + b[p][2] * b[p][2];
             const float be = b[q][0] * b[q][0] + b[q][1] * b[q][1] + b[q][2] * b[q][2];
             const float ga = b[p][0] * b[q][0] + b[p][1] * b[q][1] + b[p][2] * b[q][2];
-            if (fabsf(ga) > 1e-20f && ga * ga > 1e-15f * al * be) {
-                const float zeta = (be - al) / (2.f * ga);
-                const float t = copysignf(1.f, zeta) / (fabsf(zeta) + sqrtf(1.f + zeta * zeta));
-                const float cs = 1.f / sqrtf(1.f + t * t);
-                const float sn = cs * t;
+            if (fabsf(ga) > 1e-20f && ga * ga > 1e-13f * al * be) {
+                rotated = true;
+                const float d = be - al, g = 2.f * ga;
+                const float hh = d * d + g * g;
+                float rh = rsqrtf(hh);
+                rh = rh * (1.5f - 0.5f * hh * rh * rh);
+                const float c2 = 0.5f + 0.5f * fabsf(d) * rh;
+                float rc = rsqrtf(c2);
+                rc = rc * (1.5f - 0.5f * c2 * rc * rc);
+                const float cs = c2 * rc;
+                const float sn = copysignf(0.5f, d) * g * rh * rc;
 #pragma unroll
                 for (int r = 0; r < 3; ++r) {
                     const float bp = b[p][r], bq = b[q][r];
@@ -90,6 +102,7 @@ __device__ __forceinline__ void svd3(const M3& F, M3& U, V3& sig, M3& V) {
                 }
             }
         }
+        if (!rotated) break;
     }
     float n[3];
 #pragma unroll

@@ -151,7 +151,7 @@ def test_conservation_at_full_size(built_lib, cuda_dev):
     s.p2g2p_n(100, 1e-4)
     torch.cuda.synchronize()
     p1 = (m[:, None] * s.mpm_state.particle_v.numpy()).sum(0)
-    assert np.abs(p1 - p0).max() < 2e-4 * np.abs(m[:, None] * sc["v"]).sum()
+    assert np.abs(p1 - p0).max() < 1e-8 * np.abs(m[:, None] * sc["v"]).sum()      # measured 1.0e-10 (fp32 atomics rounding only)
     x = s.mpm_state.particle_x.numpy()
     assert np.isfinite(x).all() and x.min() > 0.5 and x.max() < 1.5
 
