@@ -162,7 +162,7 @@ def setup_oracle_mpm(sc, ng, parallel=1, precision="f32"):
 def run_mpm_slab_block(args, rank, world, dev, pk):
     """BASELINE.json configs[4]: ONE 1M-particle scene on a 256^3 grid, strong scaling over the ranks. N = 1 runs the
     undivided scene; N > 1 shards it into x-slabs with (nearly) equal particle counts: the overlap sums are exchanged on
-    the device (halo kernel reading the neighbours' grids over NVLink after a flag handshake), particle migration every
+    the device (the grid sweep adds the neighbours' partial sums straight from their memory over NVLink after one flag handshake), particle migration every
     `migrate_every` substeps goes through NCCL send/recv. Returns the dict reported under "mpm_slab" (rank 0) or None."""
     import contextlib
     import torch.distributed as dist
@@ -271,14 +271,14 @@ def run_mpm_slab_block(args, rank, world, dev, pk):
     ms = float(t.item())
     algo = 212.0 * n + 56.0 * G ** 3                                  # 1.15 GB per substep at 1M / 256^3
     ach = algo * sub / (ms * 1e-3) * 1e-9
-    # node box of the particles (yz extent) x shared planes x 16 B: what one halo kernel reads from ONE neighbour per substep
+    # node box of the particles (yz extent) x shared planes x 16 B: what one grid sweep reads from ONE neighbour per substep
     ext = [int(np.floor(sc["x"][:, a].max() * G / lim - 0.5)) + 3 - int(np.floor(sc["x"][:, a].min() * G / lim - 0.5)) + 4 for a in (1, 2)]
     return {"metric": "mpm_particle_steps_per_s", "value": n * sub / (ms * 1e-3), "unit": "particle-steps/s", "us_per_substep": ms / sub * 1e3,
             "scaling": "strong", "substeps": sub, "particles": n, "grid": G, "particles_after": int(cnt.item()),
             "state_finite_and_in_bounds": bool(fin.item() > 0), "vs_single_domain_run": vs_single, "dt": dt, "max_particles_per_rank": int(mx.item()), "slab_bounds": bounds, "slack_planes": slack, "migrate_every": migrate_every,
             "lazy_trigger_planes": lazy, "migration_checks_in_timed_region": checks, "migrations_in_timed_region": migrations,
             "exchange": ("none (undivided scene)" if world == 1 else
-                         "device-side: halo kernel reads the neighbour's partial sums over NVLink (cudaIpc-mapped grids, flag handshake); "
+                         "device-side: the grid sweep reads the neighbours' partial sums over NVLink (cudaIpc-mapped grids, one flag handshake per substep); "
                          "migration over NCCL send/recv"),
             "halo_bytes_per_substep_per_neighbour": 0 if world == 1 else (2 + 2 * slack) * ext[0] * ext[1] * 16,
             "roofline": {"bound": "hbm", "achieved": ach, "peak": pk["hbm"] * world, "unit": "GB/s", "frac": ach / (pk["hbm"] * world),

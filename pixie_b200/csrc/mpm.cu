@@ -9,7 +9,7 @@
 //                        the particles' node box; clears the {mv, m} nodes it consumed (zero_grid fused away); advances the
 //                        clock and the moving cuboids (the reference's host-side `modify`, mpm_solver_warp.py:899-905,
 //                        and `self.time += dt`, :637)
-// Slab-decomposed runs add mpm_halo_kernel between the two (device-side overlap exchange).  This file holds the small setup /
+// In slab-decomposed runs the grid sweep also adds the neighbours' partial sums on the shared planes (device-side exchange).  This file holds the small setup /
 // export kernels (on the caller's arrays) and the host side.
 #include "mpm.cuh"
 #include "mpm_math.cuh"

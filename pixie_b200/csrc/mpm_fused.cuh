@@ -246,7 +246,7 @@ mpm_fused_kernel(const __grid_constant__ FusedState s, const float dt) {
     // for the previous one (its grid velocities / the particle state it wrote) — no-ops in a plain launch
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    // slab mode: one scattering launch per substep advances the substep counter (nothing in THIS launch reads it; the halo
+    // slab mode: one scattering launch per substep advances the substep counter (nothing in THIS launch reads it; the grid
     // and grid kernels behind it in the stream do)
     if (s.slab_step && s.do_p2g && blockIdx.x == 0 && threadIdx.x == 0) *s.slab_step = *s.slab_step + 1;
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -485,7 +485,7 @@ struct SlabFlags {
 static_assert(sizeof(SlabFlags) == 256, "SlabFlags layout");
 
 // Phase API only (a single-process driver sequences the phases of SEVERAL slabs on one stream and must raise every slab's
-// scatter_done before the first halo launch waits): one thread raises the flag after the particle kernel in front of it.
+// scatter_done before the first grid sweep waits): one thread raises the flag after the particle kernel in front of it.
 __global__ void mpm_publish_kernel(SlabFlags* mine) {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");

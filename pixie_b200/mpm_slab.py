@@ -5,13 +5,14 @@ shards ONE simulation along x: rank r owns grid planes [x0, x1) and the particle
 (`int(x/dx - 0.5)`, mpm_utils.py:344) lies there. One substep is
 
     scatter   every rank scatters its particles into its own full-size {mv, m} grid (g2p of the previous substep fused in)
-    halo      the partial sums of the planes two neighbours both touch are added: total = own + neighbour
+    exchange  the partial sums of the planes two neighbours both touch are added: total = own + neighbour (on the CUDA backend
+              inside the grid sweep of `finish`, straight from the neighbour's memory)
     finish    every rank normalises / applies the BCs on its owned + overlap planes
 
 and every `migrate_every` substeps particles whose base plane left [x0, x1) move to the neighbour (packed records over
 send/recv, live prefix of the bound arrays shrinks / grows). `slack` is how many planes a particle may drift outside
 its slab between two migrations; the overlap with the right neighbour is [x1 - slack, x1 + 2 + slack) because a particle
-touches planes base .. base+2. After the halo both neighbours hold the COMPLETE sums on the overlap, so the grid
+touches planes base .. base+2. After the exchange both neighbours hold the COMPLETE sums on the overlap, so the grid
 update there is computed redundantly and no second exchange is needed.
 
 Two exchange mechanisms behind one orchestration:
@@ -115,7 +116,7 @@ class FusedSlabBackend:
         self._phase(2, dt)
 
     def step(self, n: int, dt: float):
-        """`n` whole substeps (scatter, halo, finish chained on the device, replayed from a CUDA graph)."""
+        """`n` whole substeps (scatter and sweep chained on the device, replayed from a CUDA graph)."""
         self.solver.p2g2p_n(n, dt)
 
     def error(self) -> int:
