@@ -157,12 +157,10 @@ __device__ __forceinline__ void svd3(const M3& F, M3& U, V3& sig, M3& V) {
 // Returns false (caller falls back to svd3) if det F <= 0 or the iteration does not settle.
 __device__ __forceinline__ bool polar_rotation(const M3& F, M3& R) {
     R = F;
-    float det = m3_det(R);
-    if (!(det > 1e-12f)) return false;
     bool last = false;
 #pragma unroll 1
     for (int it = 0; it < 12; ++it) {
-        // cofactor matrix: inv(R)^T = cof(R) / det(R)
+        // cofactor matrix: inv(R)^T = cof(R) / det(R); det(R) is the first row of R times the first row of cof(R)
         M3 cof;
         cof.m[0] = R.m[4] * R.m[8] - R.m[5] * R.m[7];
         cof.m[1] = R.m[5] * R.m[6] - R.m[3] * R.m[8];
@@ -173,9 +171,11 @@ __device__ __forceinline__ bool polar_rotation(const M3& F, M3& R) {
         cof.m[6] = R.m[1] * R.m[5] - R.m[2] * R.m[4];
         cof.m[7] = R.m[2] * R.m[3] - R.m[0] * R.m[5];
         cof.m[8] = R.m[0] * R.m[4] - R.m[1] * R.m[3];
+        const float det = R.m[0] * cof.m[0] + R.m[1] * cof.m[1] + R.m[2] * cof.m[2];
+        if (!(det > 1e-12f)) return false;
         // scaling g = det^(-1/3) speeds up the first steps; g -> 1 as R approaches a rotation
         const float g = (it < 2 && !last) ? rcbrtf(det) : 1.0f;
-        const float a = 0.5f * g, b = 0.5f / (g * det);
+        const float a = 0.5f * g, b = __fdividef(0.5f, g * det);
         float delta = 0.f;
         M3 N;
 #pragma unroll
@@ -185,8 +185,6 @@ __device__ __forceinline__ bool polar_rotation(const M3& F, M3& R) {
         }
         R = N;
         if (last) return true;
-        det = m3_det(R);
-        if (!(det > 1e-12f)) return false;
         // quadratic convergence: once a step moves entries by < 3e-4 the next (unscaled) step is exact to fp32
         if (delta < 3e-4f) last = true;
     }
