@@ -85,6 +85,32 @@ def test_lazy_migration_matches_single_domain_and_migrates_less():
         _oracle_rank(fields, world, 0, 2, slack=2, lazy_trigger=3)
 
 
+def test_balanced_slab_bounds_properties():
+    """Cuts at the particle quantiles: contiguous cover of [0, n_grid), every slab at least min_width planes, particle counts
+    within a plane's worth of each other; the block of BASELINE configs[4] (particles on 40 % of the x range) must not leave
+    ranks empty the way equal-width slabs do."""
+    from pixie_b200.mpm_slab import balanced_slab_bounds
+    rng = np.random.default_rng(0)
+    n_grid, n = 256, 200_000
+    base = rng.integers(77, 179, size=n)                       # stencil base planes of a 0.4-wide block
+    for world in (2, 3, 4, 8):
+        b = balanced_slab_bounds(base, n_grid, world, 6)
+        assert b[0][0] == 0 and b[-1][1] == n_grid and all(b[i][1] == b[i + 1][0] for i in range(world - 1))
+        assert all(x1 - x0 >= 6 for x0, x1 in b)
+        counts = [int(((base >= (x0 if i else -1)) & (base < (x1 if i < world - 1 else n_grid + 1))).sum()) for i, (x0, x1) in enumerate(b)]
+        assert sum(counts) == n and min(counts) > 0
+        per_plane = n / 102
+        assert max(counts) - min(counts) <= 2 * per_plane + 1, (world, counts)
+        equal = [int(((base >= r * n_grid // world) & (base < (r + 1) * n_grid // world)).sum()) for r in range(world)]
+        assert max(counts) <= max(equal) + per_plane + 1                      # never worse than equal-width slabs (up to one plane)
+    # a domain that cannot hold that many slabs of the minimum width is an error, not a silent squeeze
+    with pytest.raises(ValueError):
+        balanced_slab_bounds(base, 16, 4, 6)
+    # degenerate input: all particles on one plane -> widths still legal, cover still complete
+    b = balanced_slab_bounds(np.full(1000, 128), n_grid, 4, 6)
+    assert b[0][0] == 0 and b[-1][1] == n_grid and all(x1 - x0 >= 6 for x0, x1 in b)
+
+
 def test_slab_too_narrow_is_rejected():
     from slab_backends import OracleSlabBackend
     b = OracleSlabBackend(8, 1.0, 4, "f64")
